@@ -1,0 +1,306 @@
+"""ctypes binding of the C-ABI library (include/cornelis_cuda.h) — what tests/ and bench.py drive.
+
+There is no fallback: if cornelis_b200/lib/libcornelis_cuda.so is missing, importing a symbol from here raises, and
+every compute call fails with CORNELIS_ERR_NO_DEVICE on a machine without a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libcornelis_cuda.so"
+
+# every symbol include/cornelis_cuda.h declares
+EXPORTS = [
+    "cornelis_cuda_abi_version", "cornelis_cuda_last_error", "cornelis_cuda_device_count",
+    "cornelis_cuda_scene_create", "cornelis_cuda_scene_destroy", "cornelis_cuda_scene_set_stream", "cornelis_cuda_render_accumulate",
+    "cornelis_cuda_framebuffer_device", "cornelis_cuda_resolve", "cornelis_cuda_resolve_srgb8",
+    "cornelis_cuda_render", "cornelis_cuda_pixel_rays", "cornelis_cuda_intersect",
+    "cornelis_cuda_intersect_device", "cornelis_cuda_bsdf_sample", "cornelis_cuda_bsdf_eval",
+    "cornelis_cuda_shade", "cornelis_cuda_rng_uniforms",
+]
+
+OK, ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_ABORTED = range(6)
+RENDER_VARIANCE, RENDER_KEEP, RENDER_STAGE_TIMING, RENDER_DROP_NONFINITE = 1, 2, 4, 8
+PIPELINE_DEFAULT, PIPELINE_WAVEFRONT = 0, 1
+DEFAULT_SEED = 19791102
+
+
+class CameraDesc(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("look_at", C.c_float * 3), ("aspect", C.c_float),
+                ("horizontal_fov", C.c_float)]
+
+
+class MaterialDesc(C.Structure):
+    _fields_ = [("albedo", C.c_float * 3), ("emissive", C.c_float * 3), ("roughness", C.c_float),
+                ("reflection_tint", C.c_float * 3), ("ior", C.c_float)]
+
+
+class SphereDesc(C.Structure):
+    _fields_ = [("center", C.c_float * 3), ("radius", C.c_float), ("material", C.c_int32)]
+
+
+class PlaneDesc(C.Structure):
+    _fields_ = [("normal", C.c_float * 3), ("point", C.c_float * 3), ("extents", C.c_float * 3),
+                ("material", C.c_int32)]
+
+
+class RenderParams(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("samples", C.c_int32), ("first_sample", C.c_int32),
+                ("sample_count", C.c_int32), ("max_depth", C.c_int32), ("seed", C.c_uint64), ("flags", C.c_uint32),
+                ("pipeline", C.c_int32), ("pool_paths", C.c_int32), ("reserved", C.c_int32)]
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("pixel_samples", C.c_uint64), ("rays", C.c_uint64), ("shaded_hits", C.c_uint64),
+                ("iterations", C.c_uint64), ("kernel_launches", C.c_uint64), ("max_depth", C.c_uint32),
+                ("reserved", C.c_uint32), ("gpu_ms", C.c_float), ("intersect_ms", C.c_float),
+                ("shade_ms", C.c_float), ("raygen_ms", C.c_float), ("accumulate_ms", C.c_float)]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved"}
+
+
+PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64)
+
+
+class CornelisError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"cornelis_cuda error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Loads the C-ABI library (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise FileNotFoundError(f"{LIB_PATH} is missing — run `python cornelis_b200/build.py` "
+                                    "(there is no CPU fallback)")
+        L = C.CDLL(os.fspath(LIB_PATH))
+        L.cornelis_cuda_last_error.restype = C.c_char_p
+        vp, sz, i32, f = C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p
+        L.cornelis_cuda_device_count.argtypes = [C.POINTER(C.c_int)]
+        L.cornelis_cuda_scene_create.argtypes = [C.c_int, C.POINTER(CameraDesc), vp, sz, vp, sz, vp, sz, C.POINTER(vp)]
+        L.cornelis_cuda_scene_destroy.argtypes = [vp]
+        L.cornelis_cuda_scene_set_stream.argtypes = [vp, vp]
+        L.cornelis_cuda_render_accumulate.argtypes = [vp, C.POINTER(RenderParams), vp, vp, C.POINTER(RenderStats)]
+        L.cornelis_cuda_framebuffer_device.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
+        L.cornelis_cuda_resolve.argtypes = [vp, i32, vp, vp]
+        L.cornelis_cuda_resolve_srgb8.argtypes = [vp, i32, vp]
+        L.cornelis_cuda_render.argtypes = [vp, C.POINTER(RenderParams), vp, C.POINTER(RenderStats)]
+        L.cornelis_cuda_pixel_rays.argtypes = [vp, i32, i32, sz, f, f, f, f, f, f]
+        L.cornelis_cuda_intersect.argtypes = [vp, sz, f, f, f, f, f, f, f]
+        L.cornelis_cuda_intersect_device.argtypes = [vp, sz, vp, vp, vp, C.c_int, C.POINTER(C.c_float)]
+        L.cornelis_cuda_bsdf_sample.argtypes = [vp, sz, f, f, f, f, f, f, f]
+        L.cornelis_cuda_bsdf_eval.argtypes = [vp, sz, f, f, f, f, f, f]
+        L.cornelis_cuda_shade.argtypes = [vp, sz, i32, f, f, f, f, f, f, f, f, f]
+        L.cornelis_cuda_rng_uniforms.argtypes = [vp, C.c_uint64, sz, f, f, f, f]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise CornelisError(rc, lib().cornelis_cuda_last_error().decode())
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    _check(lib().cornelis_cuda_device_count(C.byref(n)))
+    return n.value
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a if shape is None else a.reshape(shape)
+
+
+# MaterialDescription{} (reference SceneDescription.hpp:14-20): scene material 0
+DEFAULT_MATERIAL = [0.5, 0.5, 0.5, 0, 0, 0, 0.2, 0, 0, 0, 1.5]
+
+
+class Scene:
+    """A scene resident on one GPU: SceneData (reference Scene.cpp:40-53) uploaded behind the C-ABI."""
+
+    def __init__(self, flat, device: int = 0):
+        self.handle = None
+        L = lib()
+        cam = CameraDesc()
+        c = _f32(flat["camera"], (8,))
+        cam.origin[:] = c[0:3]
+        cam.look_at[:] = c[3:6]
+        cam.aspect, cam.horizontal_fov = float(c[6]), float(c[7])
+        sph = _f32(flat["spheres"], (-1, 4))
+        smat = np.asarray(flat["sphere_mat"], np.int32)
+        pl = _f32(flat["planes"], (-1, 9))
+        pmat = np.asarray(flat["plane_mat"], np.int32)
+        mats = np.concatenate([np.asarray([DEFAULT_MATERIAL], np.float32), _f32(flat["materials"], (-1, 11))])
+        S = (SphereDesc * max(len(sph), 1))()
+        for i, (row, m) in enumerate(zip(sph, smat)):
+            S[i].center[:] = row[0:3]
+            S[i].radius = float(row[3])
+            S[i].material = int(m)
+        P = (PlaneDesc * max(len(pl), 1))()
+        for i, (row, m) in enumerate(zip(pl, pmat)):
+            P[i].normal[:] = row[0:3]
+            P[i].point[:] = row[3:6]
+            P[i].extents[:] = row[6:9]
+            P[i].material = int(m)
+        M = (MaterialDesc * len(mats))()
+        for i, row in enumerate(mats):
+            M[i].albedo[:] = row[0:3]
+            M[i].emissive[:] = row[3:6]
+            M[i].roughness = float(row[6])
+            M[i].reflection_tint[:] = row[7:10]
+            M[i].ior = float(row[10])
+        self.n_spheres, self.n_planes, self.n_materials = len(sph), len(pl), len(mats)
+        self.scene_bytes = C.sizeof(cam) + C.sizeof(SphereDesc) * len(sph) + C.sizeof(PlaneDesc) * len(pl) + \
+            C.sizeof(MaterialDesc) * len(mats)
+        h = C.c_void_p()
+        _check(L.cornelis_cuda_scene_create(device, C.byref(cam), S, len(sph), P, len(pl), M, len(mats), C.byref(h)))
+        self.handle = h
+        self.device = device
+        self.frame = None
+
+    def close(self):
+        if self.handle:
+            lib().cornelis_cuda_scene_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int | None):
+        """Run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); None = the scene's own."""
+        _check(lib().cornelis_cuda_scene_set_stream(self.handle, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    # ---- hot path --------------------------------------------------------------------------------------------------
+    def _params(self, width, height, samples, first_sample=0, sample_count=0, max_depth=0, seed=DEFAULT_SEED,
+                variance=False, keep=False, stage_timing=False, drop_nonfinite=False, pipeline=PIPELINE_DEFAULT,
+                pool_paths=0):
+        p = RenderParams()
+        p.width, p.height, p.samples = width, height, samples
+        p.first_sample, p.sample_count, p.max_depth = first_sample, sample_count, max_depth
+        p.seed = seed
+        p.flags = (RENDER_VARIANCE if variance else 0) | (RENDER_KEEP if keep else 0) | \
+            (RENDER_STAGE_TIMING if stage_timing else 0) | (RENDER_DROP_NONFINITE if drop_nonfinite else 0)
+        p.pipeline, p.pool_paths = pipeline, pool_paths
+        return p
+
+    def render_accumulate(self, width, height, samples, progress=None, **kw):
+        """Renders into the device accumulators; returns the stats dict."""
+        p = self._params(width, height, samples, **kw)
+        st = RenderStats()
+        cb = PROGRESS_FN(lambda user, done, total: int(progress(done, total) or 0)) if progress else None
+        _check(lib().cornelis_cuda_render_accumulate(self.handle, C.byref(p), C.cast(cb, C.c_void_p) if cb else None,
+                                                     None, C.byref(st)))
+        self.frame = (width, height)
+        return st.as_dict()
+
+    def framebuffer_device(self):
+        """(device pointer, float count) of the float4 accumulation image."""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        _check(lib().cornelis_cuda_framebuffer_device(self.handle, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def resolve(self, samples, variance=False, out=None):
+        W, H = self.frame
+        rgb = out if out is not None else np.empty((H, W, 3), np.float32)
+        var = np.empty((H, W, 3), np.float32) if variance else None
+        _check(lib().cornelis_cuda_resolve(self.handle, samples, _ptr(rgb), _ptr(var)))
+        return (rgb, var) if variance else rgb
+
+    def resolve_srgb8(self, samples):
+        W, H = self.frame
+        out = np.empty((H, W, 3), np.uint8)
+        _check(lib().cornelis_cuda_resolve_srgb8(self.handle, samples, _ptr(out)))
+        return out
+
+    def render(self, width, height, samples, out=None, out_ptr=None, **kw):
+        """The end-to-end call: render and download the framebuffer into host memory."""
+        p = self._params(width, height, samples, **kw)
+        st = RenderStats()
+        if out_ptr is None:
+            out = out if out is not None else np.empty((height, width, 3), np.float32)
+            out_ptr = _ptr(out)
+        _check(lib().cornelis_cuda_render(self.handle, C.byref(p), out_ptr, C.byref(st)))
+        self.frame = (width, height)
+        return out, st.as_dict()
+
+    # ---- stages ------------------------------------------------------------------------------------------------------
+    def pixel_rays(self, W, H, pi, pj, phi1, phi2):
+        pi, pj = np.ascontiguousarray(pi, np.int32), np.ascontiguousarray(pj, np.int32)
+        phi1, phi2 = _f32(phi1), _f32(phi2)
+        n = len(pi)
+        org, dirs = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+        _check(lib().cornelis_cuda_pixel_rays(self.handle, W, H, n, _ptr(pi), _ptr(pj), _ptr(phi1), _ptr(phi2),
+                                              _ptr(org), _ptr(dirs)))
+        return org, dirs
+
+    def intersect(self, org, dirs, surface=True):
+        org, dirs = _f32(org, (-1, 3)), _f32(dirs, (-1, 3))
+        n = len(org)
+        t, prim = np.empty(n, np.float32), np.empty(n, np.int32)
+        P = np.empty((n, 3), np.float32) if surface else None
+        N = np.empty((n, 3), np.float32) if surface else None
+        mat = np.empty(n, np.int32) if surface else None
+        _check(lib().cornelis_cuda_intersect(self.handle, n, _ptr(org), _ptr(dirs), _ptr(t), _ptr(prim), _ptr(P), _ptr(N),
+                                             _ptr(mat)))
+        return dict(t=t, prim=prim, P=P, N=N, mat=mat)
+
+    def intersect_device(self, n, d_org4, d_dir4, d_hit2, repeats=1):
+        ms = C.c_float(0)
+        _check(lib().cornelis_cuda_intersect_device(self.handle, n, d_org4, d_dir4, d_hit2, repeats, C.byref(ms)))
+        return ms.value
+
+    def bsdf_sample(self, mat, wo, N, x):
+        mat = np.ascontiguousarray(mat, np.int32)
+        wo, N, x = _f32(wo, (-1, 3)), _f32(N, (-1, 3)), _f32(x, (-1, 3))
+        n = len(mat)
+        wi, pdf, f = np.empty((n, 3), np.float32), np.empty(n, np.float32), np.empty((n, 3), np.float32)
+        _check(lib().cornelis_cuda_bsdf_sample(self.handle, n, _ptr(mat), _ptr(wo), _ptr(N), _ptr(x), _ptr(wi), _ptr(pdf),
+                                               _ptr(f)))
+        return dict(wi=wi, pdf=pdf, f=f)
+
+    def bsdf_eval(self, mat, wi, wo, N):
+        mat = np.ascontiguousarray(mat, np.int32)
+        wi, wo, N = _f32(wi, (-1, 3)), _f32(wo, (-1, 3)), _f32(N, (-1, 3))
+        n = len(mat)
+        f, pdf = np.empty((n, 3), np.float32), np.empty(n, np.float32)
+        _check(lib().cornelis_cuda_bsdf_eval(self.handle, n, _ptr(mat), _ptr(wi), _ptr(wo), _ptr(N), _ptr(f), _ptr(pdf)))
+        return dict(f=f, pdf=pdf)
+
+    def shade(self, depth, u, P, N, mat, org, dirs, thr, rad):
+        """u[n,4] = (RR draw, x0, x1, x2)."""
+        mat = np.ascontiguousarray(mat, np.int32)
+        u, P, N = _f32(u, (-1, 4)), _f32(P, (-1, 3)), _f32(N, (-1, 3))
+        org, dirs = _f32(org, (-1, 3)).copy(), _f32(dirs, (-1, 3)).copy()
+        thr, rad = _f32(thr, (-1, 3)).copy(), _f32(rad, (-1, 3)).copy()
+        n = len(mat)
+        alive = np.empty(n, np.uint8)
+        _check(lib().cornelis_cuda_shade(self.handle, n, depth, _ptr(u), _ptr(P), _ptr(N), _ptr(mat), _ptr(org),
+                                         _ptr(dirs), _ptr(thr), _ptr(rad), _ptr(alive)))
+        return dict(org=org, dir=dirs, thr=thr, rad=rad, alive=alive.astype(bool))
+
+    def rng_uniforms(self, seed, pixel, sample, block):
+        pixel = np.ascontiguousarray(pixel, np.uint32)
+        sample = np.ascontiguousarray(sample, np.uint32)
+        block = np.ascontiguousarray(block, np.uint32)
+        out = np.empty((len(pixel), 4), np.float32)
+        _check(lib().cornelis_cuda_rng_uniforms(self.handle, seed, len(pixel), _ptr(pixel), _ptr(sample), _ptr(block),
+                                                _ptr(out)))
+        return out

@@ -1,0 +1,742 @@
+// C-ABI of the render path (include/cornelis_cuda.h): scene upload, wavefront driver, stage entry points.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/cornelis_cuda.h"
+#include "device_types.h"
+#include "materials.cuh"
+#include "math.cuh"
+#include "wavefront.h"
+
+using namespace cornelis_b200;
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int fail(cornelis_status code, const std::string &message) {
+    g_lastError = message;
+    return code;
+}
+
+#define CB_CUDA(expr)                                                                                                  \
+    do {                                                                                                               \
+        cudaError_t e_ = (expr);                                                                                       \
+        if (e_ != cudaSuccess)                                                                                         \
+            return fail(e_ == cudaErrorMemoryAllocation ? CORNELIS_ERR_OUT_OF_MEMORY : CORNELIS_ERR_CUDA,               \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));                                          \
+    } while (0)
+
+template <typename T>
+struct DeviceBuffer {
+    T *ptr = nullptr;
+    size_t count = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= count)
+            return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ptr), n * sizeof(T));
+        if (e == cudaSuccess)
+            count = n;
+        else
+            ptr = nullptr;
+        return e;
+    }
+    void release() {
+        if (ptr)
+            cudaFree(ptr);
+        ptr = nullptr;
+        count = 0;
+    }
+};
+
+// PerspectiveCamera::lookAt, reference src/Camera.cpp:15-34, over nanovdb::Vec3<float> semantics
+// (NanoVDB.h:911-953): cross = (a1 b2 - a2 b1, ...), normalize = multiply by the rounded reciprocal length,
+// `0.5 * u` evaluated in double (exact halving).
+DevCamera makeCamera(const cornelis_camera_desc &c) {
+    V3 const from{c.origin[0], c.origin[1], c.origin[2]}, at{c.look_at[0], c.look_at[1], c.look_at[2]};
+    V3 const up{0.0f, 1.0f, 0.0f};
+    V3 dir = at - from;
+    {
+        float s = 1.0f / sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+        dir = V3{dir.x * s, dir.y * s, dir.z * s};
+    }
+    V3 u = cross(up, dir);
+    V3 v = cross(u, dir);
+    float const fovScale = static_cast<float>(2.0 * std::sin(c.horizontal_fov * 0.5));
+    u = V3{u.x * fovScale, u.y * fovScale, u.z * fovScale};
+    float const vs = c.aspect * fovScale;
+    v = V3{v.x * vs, v.y * vs, v.z * vs};
+    V3 const hu{static_cast<float>(0.5 * u.x), static_cast<float>(0.5 * u.y), static_cast<float>(0.5 * u.z)};
+    V3 const hv{static_cast<float>(0.5 * v.x), static_cast<float>(0.5 * v.y), static_cast<float>(0.5 * v.z)};
+    V3 const corner = (dir - hu) - hv;
+    DevCamera cam{};
+    cam.ex = from.x, cam.ey = from.y, cam.ez = from.z;
+    cam.cx = corner.x, cam.cy = corner.y, cam.cz = corner.z;
+    cam.ux = u.x, cam.uy = u.y, cam.uz = u.z;
+    cam.vx = v.x, cam.vy = v.y, cam.vz = v.z;
+    return cam;
+}
+
+} // namespace
+
+struct cornelis_cuda_scene {
+    int device = 0;
+    cudaStream_t stream = nullptr;    // the stream in use
+    cudaStream_t ownStream = nullptr; // created with the scene
+    LaunchShape shape;
+    // scene tables
+    DeviceBuffer<DevSphere> spheres;
+    DeviceBuffer<uint32_t> sphereMaterial;
+    DeviceBuffer<DevPlane> planes;
+    DeviceBuffer<DevMaterial> materials;
+    SceneView view{};
+    // wavefront state
+    uint32_t width = 0, height = 0;
+    DeviceBuffer<float4> pool[2][4];
+    DeviceBuffer<HitRecord> hits;
+    DeviceBuffer<uint32_t> hitQueue;
+    DeviceBuffer<FinishedPath> finished;
+    DeviceBuffer<Control> control;
+    Control *hostControl = nullptr; // pinned
+    DeviceBuffer<float4> accum, accum2;
+    bool haveVariance = false;
+    DeviceBuffer<float> outRgb, outVar;
+    DeviceBuffer<uint8_t> outRgb8;
+    // staging for the stage entry points
+    DeviceBuffer<float> stageF[12];
+    DeviceBuffer<int32_t> stageI[3];
+    DeviceBuffer<float4> stage4[2];
+    DeviceBuffer<HitRecord> stageHits;
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    cudaEvent_t evStage[6] = {};
+
+    ~cornelis_cuda_scene() {
+        cudaSetDevice(device);
+        if (stream)
+            cudaStreamSynchronize(stream);
+        spheres.release(), sphereMaterial.release(), planes.release(), materials.release();
+        for (auto &half : pool)
+            for (auto &b : half)
+                b.release();
+        hits.release(), hitQueue.release(), finished.release(), control.release();
+        accum.release(), accum2.release(), outRgb.release(), outVar.release(), outRgb8.release();
+        for (auto &b : stageF)
+            b.release();
+        for (auto &b : stageI)
+            b.release();
+        for (auto &b : stage4)
+            b.release();
+        stageHits.release();
+        if (hostControl)
+            cudaFreeHost(hostControl);
+        if (evStart)
+            cudaEventDestroy(evStart);
+        if (evStop)
+            cudaEventDestroy(evStop);
+        for (auto &e : evStage)
+            if (e)
+                cudaEventDestroy(e);
+        if (ownStream)
+            cudaStreamDestroy(ownStream);
+    }
+};
+
+namespace {
+
+PathPool poolView(cornelis_cuda_scene *s, int which) {
+    return PathPool{s->pool[which][0].ptr, s->pool[which][1].ptr, s->pool[which][2].ptr, s->pool[which][3].ptr};
+}
+
+int ensureFrame(cornelis_cuda_scene *s, uint32_t width, uint32_t height, uint32_t poolPaths, bool variance) {
+    size_t const npix = static_cast<size_t>(width) * height;
+    for (int half = 0; half < 2; half++)
+        for (int a = 0; a < 4; a++)
+            CB_CUDA(s->pool[half][a].reserve(poolPaths));
+    CB_CUDA(s->hits.reserve(poolPaths));
+    CB_CUDA(s->hitQueue.reserve(poolPaths));
+    CB_CUDA(s->finished.reserve(2 * static_cast<size_t>(poolPaths)));
+    CB_CUDA(s->control.reserve(1));
+    if (!s->hostControl)
+        CB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&s->hostControl), sizeof(Control)));
+    bool const resized = s->width != width || s->height != height;
+    if (resized) {
+        s->accum.release();
+        s->accum2.release();
+        s->haveVariance = false;
+    }
+    CB_CUDA(s->accum.reserve(npix));
+    if (variance)
+        CB_CUDA(s->accum2.reserve(npix));
+    s->width = width;
+    s->height = height;
+    return CORNELIS_OK;
+}
+
+int checkScene(cornelis_cuda_scene *s) {
+    if (!s)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "scene handle is null");
+    CB_CUDA(cudaSetDevice(s->device));
+    return CORNELIS_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int cornelis_cuda_abi_version(void) { return CORNELIS_CUDA_ABI_VERSION; }
+
+const char *cornelis_cuda_last_error(void) { return g_lastError.c_str(); }
+
+int cornelis_cuda_device_count(int *count) {
+    if (!count)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "count is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        *count = 0;
+        return fail(CORNELIS_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                                " (this library has no CPU path)");
+    }
+    *count = n;
+    return CORNELIS_OK;
+}
+
+int cornelis_cuda_scene_create(int device, const cornelis_camera_desc *camera, const cornelis_sphere_desc *spheres,
+                               size_t n_spheres, const cornelis_plane_desc *planes, size_t n_planes,
+                               const cornelis_material_desc *materials, size_t n_materials,
+                               cornelis_cuda_scene **out_scene) {
+    if (!out_scene)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "out_scene is null");
+    *out_scene = nullptr;
+    if (!camera || (n_spheres && !spheres) || (n_planes && !planes) || !materials || n_materials == 0)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "scene arrays missing (at least the default material is required)");
+    int count = 0;
+    if (int rc = cornelis_cuda_device_count(&count))
+        return rc;
+    if (device < 0 || device >= count)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "device index out of range");
+    for (size_t i = 0; i < n_spheres; i++)
+        if (spheres[i].material >= static_cast<int32_t>(n_materials))
+            return fail(CORNELIS_ERR_INVALID_ARGUMENT, "sphere material index out of range");
+    for (size_t i = 0; i < n_planes; i++)
+        if (planes[i].material >= static_cast<int32_t>(n_materials))
+            return fail(CORNELIS_ERR_INVALID_ARGUMENT, "plane material index out of range");
+
+    CB_CUDA(cudaSetDevice(device));
+    cornelis_cuda_scene *s = new (std::nothrow) cornelis_cuda_scene();
+    if (!s)
+        return fail(CORNELIS_ERR_OUT_OF_MEMORY, "host allocation failed");
+    s->device = device;
+    struct Guard {
+        cornelis_cuda_scene *p;
+        ~Guard() { delete p; }
+    } guard{s};
+
+    CB_CUDA(cudaStreamCreateWithFlags(&s->ownStream, cudaStreamNonBlocking));
+    s->stream = s->ownStream;
+    CB_CUDA(cudaEventCreate(&s->evStart));
+    CB_CUDA(cudaEventCreate(&s->evStop));
+    for (auto &e : s->evStage)
+        CB_CUDA(cudaEventCreate(&e));
+    cudaDeviceProp prop{};
+    CB_CUDA(cudaGetDeviceProperties(&prop, device));
+    s->shape.numSMs = prop.multiProcessorCount;
+    if (const char *env = std::getenv("CORNELIS_BLOCKS_PER_SM"))
+        s->shape.blocksPerSM = std::max(1, std::atoi(env));
+    s->shape.gridPersistent = s->shape.numSMs * s->shape.blocksPerSM;
+
+    // SphereData / PlaneData / materials (Scene.cpp:5-53) flattened to the device tables.
+    std::vector<DevSphere> hs(n_spheres);
+    std::vector<uint32_t> hsm(n_spheres);
+    for (size_t i = 0; i < n_spheres; i++) {
+        hs[i] = DevSphere{spheres[i].center[0], spheres[i].center[1], spheres[i].center[2],
+                          spheres[i].radius * spheres[i].radius};
+        hsm[i] = spheres[i].material >= 0 ? static_cast<uint32_t>(spheres[i].material) : 0u; // value_or(0)
+    }
+    std::vector<DevPlane> hp(n_planes);
+    for (size_t i = 0; i < n_planes; i++) {
+        const cornelis_plane_desc &d = planes[i];
+        Basis const b = constructBasis(V3{d.normal[0], d.normal[1], d.normal[2]}); // Geometry.cpp:165, hoisted
+        DevPlane p{};
+        p.px = d.point[0], p.py = d.point[1], p.pz = d.point[2], p.width = d.extents[0];
+        p.nx = d.normal[0], p.ny = d.normal[1], p.nz = d.normal[2], p.height = d.extents[1];
+        p.tx = b.T.x, p.ty = b.T.y, p.tz = b.T.z;
+        p.material = d.material >= 0 ? static_cast<uint32_t>(d.material) : 0u;
+        p.bx = b.B.x, p.by = b.B.y, p.bz = b.B.z;
+        hp[i] = p;
+    }
+    std::vector<DevMaterial> hm(n_materials);
+    for (size_t i = 0; i < n_materials; i++)
+        hm[i] = makeDevMaterial(materials[i].albedo, materials[i].emissive, materials[i].roughness,
+                                materials[i].reflection_tint, materials[i].ior);
+
+    CB_CUDA(s->spheres.reserve(n_spheres ? n_spheres : 1));
+    CB_CUDA(s->sphereMaterial.reserve(n_spheres ? n_spheres : 1));
+    CB_CUDA(s->planes.reserve(n_planes ? n_planes : 1));
+    CB_CUDA(s->materials.reserve(n_materials));
+    if (n_spheres) {
+        CB_CUDA(cudaMemcpyAsync(s->spheres.ptr, hs.data(), n_spheres * sizeof(DevSphere), cudaMemcpyHostToDevice, s->stream));
+        CB_CUDA(cudaMemcpyAsync(s->sphereMaterial.ptr, hsm.data(), n_spheres * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+    }
+    if (n_planes)
+        CB_CUDA(cudaMemcpyAsync(s->planes.ptr, hp.data(), n_planes * sizeof(DevPlane), cudaMemcpyHostToDevice, s->stream));
+    CB_CUDA(cudaMemcpyAsync(s->materials.ptr, hm.data(), n_materials * sizeof(DevMaterial), cudaMemcpyHostToDevice, s->stream));
+    CB_CUDA(cudaStreamSynchronize(s->stream));
+
+    s->view.spheres = s->spheres.ptr;
+    s->view.sphereMaterial = s->sphereMaterial.ptr;
+    s->view.planes = s->planes.ptr;
+    s->view.materials = s->materials.ptr;
+    s->view.nSpheres = static_cast<uint32_t>(n_spheres);
+    s->view.nPlanes = static_cast<uint32_t>(n_planes);
+    s->view.nMaterials = static_cast<uint32_t>(n_materials);
+    s->view.camera = makeCamera(*camera);
+
+    size_t const smem = sizeof(DevSphere) * n_spheres + sizeof(DevPlane) * n_planes + sizeof(DevMaterial) * n_materials +
+                        sizeof(uint32_t) * n_spheres;
+    if (smem > static_cast<size_t>(prop.sharedMemPerBlockOptin) - 1024)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT,
+                    "scene tables exceed the shared-memory staging limit of this build (" + std::to_string(smem) +
+                        " bytes)");
+    s->shape.sceneSmemBytes = smem;
+    CB_CUDA(configureKernels(smem));
+
+    guard.p = nullptr;
+    *out_scene = s;
+    return CORNELIS_OK;
+}
+
+int cornelis_cuda_scene_destroy(cornelis_cuda_scene *scene) {
+    delete scene;
+    return CORNELIS_OK;
+}
+
+int cornelis_cuda_scene_set_stream(cornelis_cuda_scene *s, void *cudaStream) {
+    if (int rc = checkScene(s))
+        return rc;
+    CB_CUDA(cudaStreamSynchronize(s->stream));
+    s->stream = cudaStream ? static_cast<cudaStream_t>(cudaStream) : s->ownStream;
+    return CORNELIS_OK;
+}
+
+int cornelis_cuda_render_accumulate(cornelis_cuda_scene *s, const cornelis_render_params *p, cornelis_progress_fn progress,
+                                    void *progressUser, cornelis_render_stats *stats) {
+    if (int rc = checkScene(s))
+        return rc;
+    if (!p)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "params is null");
+    if (p->width <= 0 || p->height <= 0)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "frame cannot be a line or the empty rectangle"); // Math.hpp:236
+    if (p->samples <= 0)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "AA samples must be > 0"); // Render.cpp:310-313
+    int32_t const sampleCount = p->sample_count > 0 ? p->sample_count : p->samples;
+    if (p->first_sample < 0 || static_cast<int64_t>(p->first_sample) + sampleCount > (1 << 24))
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "sample range must lie in [0, 2^24)");
+    uint64_t const npix64 = static_cast<uint64_t>(p->width) * static_cast<uint64_t>(p->height);
+    if (npix64 > (1ull << 31))
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "frame too large");
+
+    uint32_t pool = p->pool_paths > 0 ? static_cast<uint32_t>(p->pool_paths) : (1u << 22);
+    if (const char *env = std::getenv("CORNELIS_POOL_PATHS"))
+        if (p->pool_paths <= 0 && std::atoll(env) > 0)
+            pool = static_cast<uint32_t>(std::atoll(env));
+    uint64_t const total = npix64 * static_cast<uint64_t>(sampleCount);
+    if (pool > total)
+        pool = static_cast<uint32_t>(total);
+    pool = (pool + 255u) & ~255u;
+    bool const variance = (p->flags & CORNELIS_RENDER_VARIANCE) != 0;
+    if (int rc = ensureFrame(s, static_cast<uint32_t>(p->width), static_cast<uint32_t>(p->height), pool, variance))
+        return rc;
+
+    cudaStream_t st = s->stream;
+    bool const keep = (p->flags & CORNELIS_RENDER_KEEP) != 0;
+    if (!keep) {
+        CB_CUDA(cudaMemsetAsync(s->accum.ptr, 0, npix64 * sizeof(float4), st));
+        if (variance)
+            CB_CUDA(cudaMemsetAsync(s->accum2.ptr, 0, npix64 * sizeof(float4), st));
+        s->haveVariance = variance;
+    } else if (variance && !s->haveVariance) {
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "KEEP with VARIANCE needs a previous VARIANCE render");
+    }
+
+    RenderConfig cfg{};
+    cfg.width = static_cast<uint32_t>(p->width);
+    cfg.height = static_cast<uint32_t>(p->height);
+    cfg.npixels = static_cast<uint32_t>(npix64);
+    cfg.firstSample = static_cast<uint32_t>(p->first_sample);
+    cfg.maxDepth = p->max_depth > 0 ? static_cast<uint32_t>(p->max_depth) : 0u;
+    cfg.poolPaths = pool;
+    cfg.variance = variance;
+    cfg.key0 = static_cast<uint32_t>(p->seed);
+    cfg.key1 = static_cast<uint32_t>(p->seed >> 32);
+    cfg.dx = 1.0f / static_cast<float>(p->width);  // Render.cpp:31
+    cfg.dy = 1.0f / static_cast<float>(p->height);
+
+    Control init{};
+    init.total = total;
+    *s->hostControl = init;
+    CB_CUDA(cudaMemcpyAsync(s->control.ptr, s->hostControl, sizeof(Control), cudaMemcpyHostToDevice, st));
+
+    bool const profileStages = (p->flags & CORNELIS_RENDER_STAGE_TIMING) != 0;
+    int const profileEvery = 32;
+    float stageMs[4] = {0, 0, 0, 0};
+    uint64_t profiled = 0;
+    uint64_t launches = 0;
+
+    CB_CUDA(cudaEventRecord(s->evStart, st));
+    int cur = 0;
+    uint64_t pass = 0;
+    int const passesPerBatch = 16;
+    bool aborted = false;
+    for (;;) {
+        for (int k = 0; k < passesPerBatch; k++, pass++) {
+            PathPool const in = poolView(s, cur), out = poolView(s, cur ^ 1);
+            bool const timed = profileStages && (pass % profileEvery == profileEvery - 1);
+            launchPlan(st, s->control.ptr, cfg);
+            if (timed)
+                cudaEventRecord(s->evStage[0], st);
+            launchRaygen(st, s->shape, s->control.ptr, cfg, s->view.camera, in);
+            if (timed)
+                cudaEventRecord(s->evStage[1], st);
+            launchIntersect(st, s->shape, s->control.ptr, s->view, in, s->hits.ptr, s->hitQueue.ptr, s->finished.ptr);
+            if (timed)
+                cudaEventRecord(s->evStage[2], st);
+            launchShade(st, s->shape, s->control.ptr, cfg, s->view, in, out, s->hits.ptr, s->hitQueue.ptr,
+                        s->finished.ptr);
+            if (timed)
+                cudaEventRecord(s->evStage[3], st);
+            launchAccumulate(st, s->shape, s->control.ptr, s->finished.ptr, s->accum.ptr,
+                             variance ? s->accum2.ptr : nullptr, (p->flags & CORNELIS_RENDER_DROP_NONFINITE) != 0);
+            if (timed) {
+                cudaEventRecord(s->evStage[4], st);
+                CB_CUDA(cudaEventSynchronize(s->evStage[4]));
+                for (int g = 0; g < 4; g++) {
+                    float ms = 0;
+                    cudaEventElapsedTime(&ms, s->evStage[g], s->evStage[g + 1]);
+                    stageMs[g] += ms;
+                }
+                profiled++;
+            }
+            launches += 5;
+            cur ^= 1;
+        }
+        CB_CUDA(cudaMemcpyAsync(s->hostControl, s->control.ptr, sizeof(Control), cudaMemcpyDeviceToHost, st));
+        CB_CUDA(cudaStreamSynchronize(st));
+        Control const &c = *s->hostControl;
+        if (c.cursor >= c.total && c.nSurvive == 0)
+            break;
+        if (progress && progress(progressUser, c.cursor, c.total) != 0) {
+            aborted = true;
+            break;
+        }
+    }
+    CB_CUDA(cudaEventRecord(s->evStop, st));
+    CB_CUDA(cudaEventSynchronize(s->evStop));
+    CB_CUDA(cudaGetLastError());
+
+    if (stats) {
+        Control const &c = *s->hostControl;
+        std::memset(stats, 0, sizeof *stats);
+        stats->pixel_samples = c.cursor;
+        stats->rays = c.rays;
+        stats->shaded_hits = c.shaded;
+        stats->iterations = c.iterations;
+        stats->kernel_launches = launches;
+        stats->max_depth = c.maxDepth;
+        cudaEventElapsedTime(&stats->gpu_ms, s->evStart, s->evStop);
+        if (profiled) {
+            // mean milliseconds per launch over the sampled passes
+            stats->raygen_ms = stageMs[0] / profiled;
+            stats->intersect_ms = stageMs[1] / profiled;
+            stats->shade_ms = stageMs[2] / profiled;
+            stats->accumulate_ms = stageMs[3] / profiled;
+        }
+    }
+    if (aborted)
+        return fail(CORNELIS_ERR_ABORTED, "render aborted by the progress callback");
+    return CORNELIS_OK;
+}
+
+int cornelis_cuda_framebuffer_device(cornelis_cuda_scene *s, void **devicePtr, size_t *nFloats) {
+    if (int rc = checkScene(s))
+        return rc;
+    if (!devicePtr || !nFloats)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "null output pointer");
+    if (!s->accum.ptr || !s->width)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "nothing has been rendered yet");
+    *devicePtr = s->accum.ptr;
+    *nFloats = static_cast<size_t>(s->width) * s->height * 4;
+    return CORNELIS_OK;
+}
+
+int cornelis_cuda_resolve(cornelis_cuda_scene *s, int32_t samples, float *hostRgb, float *hostVariance) {
+    if (int rc = checkScene(s))
+        return rc;
+    if (samples <= 0 || !hostRgb)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "samples must be > 0 and host_rgb non-null");
+    if (!s->accum.ptr || !s->width)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "nothing has been rendered yet");
+    if (hostVariance && !s->haveVariance)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "variance was not accumulated (CORNELIS_RENDER_VARIANCE)");
+    size_t const npix = static_cast<size_t>(s->width) * s->height;
+    CB_CUDA(s->outRgb.reserve(3 * npix));
+    if (hostVariance)
+        CB_CUDA(s->outVar.reserve(3 * npix));
+    launchResolve(s->stream, s->shape, static_cast<uint32_t>(npix), static_cast<uint32_t>(samples), s->accum.ptr,
+                  hostVariance ? s->accum2.ptr : nullptr, s->outRgb.ptr, hostVariance ? s->outVar.ptr : nullptr);
+    CB_CUDA(cudaMemcpyAsync(hostRgb, s->outRgb.ptr, 3 * npix * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    if (hostVariance)
+        CB_CUDA(cudaMemcpyAsync(hostVariance, s->outVar.ptr, 3 * npix * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CB_CUDA(cudaStreamSynchronize(s->stream));
+    CB_CUDA(cudaGetLastError());
+    return CORNELIS_OK;
+}
+
+int cornelis_cuda_resolve_srgb8(cornelis_cuda_scene *s, int32_t samples, uint8_t *hostRgb8) {
+    if (int rc = checkScene(s))
+        return rc;
+    if (samples <= 0 || !hostRgb8)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "samples must be > 0 and host_rgb8 non-null");
+    if (!s->accum.ptr || !s->width)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "nothing has been rendered yet");
+    size_t const npix = static_cast<size_t>(s->width) * s->height;
+    CB_CUDA(s->outRgb8.reserve(3 * npix));
+    launchResolveSrgb8(s->stream, s->shape, static_cast<uint32_t>(npix), static_cast<uint32_t>(samples), s->accum.ptr,
+                       s->outRgb8.ptr);
+    CB_CUDA(cudaMemcpyAsync(hostRgb8, s->outRgb8.ptr, 3 * npix, cudaMemcpyDeviceToHost, s->stream));
+    CB_CUDA(cudaStreamSynchronize(s->stream));
+    CB_CUDA(cudaGetLastError());
+    return CORNELIS_OK;
+}
+
+int cornelis_cuda_render(cornelis_cuda_scene *s, const cornelis_render_params *p, float *hostRgb,
+                         cornelis_render_stats *stats) {
+    if (!hostRgb)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "host_rgb is null");
+    if (int rc = cornelis_cuda_render_accumulate(s, p, nullptr, nullptr, stats))
+        return rc;
+    return cornelis_cuda_resolve(s, p->samples, hostRgb, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------ stage entry points --
+
+#define UPLOAD(buf, src, count)                                                                                        \
+    do {                                                                                                               \
+        CB_CUDA((buf).reserve((count) ? (count) : 1));                                                                 \
+        CB_CUDA(cudaMemcpyAsync((buf).ptr, (src), (count) * sizeof(*(buf).ptr), cudaMemcpyHostToDevice, s->stream));   \
+    } while (0)
+#define DOWNLOAD(dst, buf, count)                                                                                      \
+    CB_CUDA(cudaMemcpyAsync((dst), (buf).ptr, (count) * sizeof(*(buf).ptr), cudaMemcpyDeviceToHost, s->stream))
+
+int cornelis_cuda_pixel_rays(cornelis_cuda_scene *s, int32_t width, int32_t height, size_t n, const int32_t *pi,
+                             const int32_t *pj, const float *phi1, const float *phi2, float *org, float *dir) {
+    if (int rc = checkScene(s))
+        return rc;
+    if (width <= 0 || height <= 0 || !pi || !pj || !phi1 || !phi2 || !org || !dir)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "bad argument");
+    if (n == 0)
+        return CORNELIS_OK;
+    UPLOAD(s->stageI[0], pi, n);
+    UPLOAD(s->stageI[1], pj, n);
+    UPLOAD(s->stageF[0], phi1, n);
+    UPLOAD(s->stageF[1], phi2, n);
+    CB_CUDA(s->stageF[2].reserve(3 * n));
+    CB_CUDA(s->stageF[3].reserve(3 * n));
+    launchPixelRays(s->stream, s->shape, s->view.camera, static_cast<uint32_t>(n), 1.0f / static_cast<float>(width),
+                    1.0f / static_cast<float>(height), s->stageI[0].ptr, s->stageI[1].ptr, s->stageF[0].ptr,
+                    s->stageF[1].ptr, s->stageF[2].ptr, s->stageF[3].ptr);
+    DOWNLOAD(org, s->stageF[2], 3 * n);
+    DOWNLOAD(dir, s->stageF[3], 3 * n);
+    CB_CUDA(cudaStreamSynchronize(s->stream));
+    CB_CUDA(cudaGetLastError());
+    return CORNELIS_OK;
+}
+
+int cornelis_cuda_intersect(cornelis_cuda_scene *s, size_t n, const float *org, const float *dir, float *t,
+                            int32_t *prim, float *P, float *N, int32_t *mat) {
+    if (int rc = checkScene(s))
+        return rc;
+    if (!org || !dir || !t || !prim)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "org, dir, t and prim are required");
+    if (n == 0)
+        return CORNELIS_OK;
+    UPLOAD(s->stageF[0], org, 3 * n);
+    UPLOAD(s->stageF[1], dir, 3 * n);
+    CB_CUDA(s->stage4[0].reserve(n));
+    CB_CUDA(s->stage4[1].reserve(n));
+    CB_CUDA(s->stageHits.reserve(n));
+    launchPack4(s->stream, s->shape, n, s->stageF[0].ptr, s->stage4[0].ptr);
+    launchPack4(s->stream, s->shape, n, s->stageF[1].ptr, s->stage4[1].ptr);
+    launchIntersectBatch(s->stream, s->shape, s->view, n, s->stage4[0].ptr, s->stage4[1].ptr, s->stageHits.ptr);
+    CB_CUDA(s->stageF[2].reserve(n));
+    CB_CUDA(s->stageI[0].reserve(n));
+    launchUnpackHits(s->stream, s->shape, n, s->stageHits.ptr, s->stageF[2].ptr, s->stageI[0].ptr);
+    DOWNLOAD(t, s->stageF[2], n);
+    DOWNLOAD(prim, s->stageI[0], n);
+    if (P || N || mat) {
+        if (P)
+            CB_CUDA(s->stageF[3].reserve(3 * n));
+        if (N)
+            CB_CUDA(s->stageF[4].reserve(3 * n));
+        if (mat)
+            CB_CUDA(s->stageI[1].reserve(n));
+        launchHitSurface(s->stream, s->shape, s->view, n, s->stage4[0].ptr, s->stage4[1].ptr, s->stageHits.ptr,
+                         P ? s->stageF[3].ptr : nullptr, N ? s->stageF[4].ptr : nullptr, mat ? s->stageI[1].ptr : nullptr);
+        if (P)
+            DOWNLOAD(P, s->stageF[3], 3 * n);
+        if (N)
+            DOWNLOAD(N, s->stageF[4], 3 * n);
+        if (mat)
+            DOWNLOAD(mat, s->stageI[1], n);
+    }
+    CB_CUDA(cudaStreamSynchronize(s->stream));
+    CB_CUDA(cudaGetLastError());
+    return CORNELIS_OK;
+}
+
+int cornelis_cuda_intersect_device(cornelis_cuda_scene *s, size_t n, const void *dOrg4, const void *dDir4, void *dHit2,
+                                   int repeats, float *msPerLaunch) {
+    if (int rc = checkScene(s))
+        return rc;
+    if (!dOrg4 || !dDir4 || !dHit2 || repeats <= 0)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "bad argument");
+    CB_CUDA(cudaEventRecord(s->evStart, s->stream));
+    for (int r = 0; r < repeats; r++)
+        launchIntersectBatch(s->stream, s->shape, s->view, n, static_cast<const float4 *>(dOrg4),
+                             static_cast<const float4 *>(dDir4), static_cast<HitRecord *>(dHit2));
+    CB_CUDA(cudaEventRecord(s->evStop, s->stream));
+    CB_CUDA(cudaEventSynchronize(s->evStop));
+    CB_CUDA(cudaGetLastError());
+    if (msPerLaunch) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, s->evStart, s->evStop);
+        *msPerLaunch = ms / repeats;
+    }
+    return CORNELIS_OK;
+}
+
+static int checkMaterialIds(cornelis_cuda_scene *s, size_t n, const int32_t *mat) {
+    for (size_t k = 0; k < n; k++)
+        if (mat[k] < 0 || static_cast<uint32_t>(mat[k]) >= s->view.nMaterials)
+            return fail(CORNELIS_ERR_INVALID_ARGUMENT, "material index out of range");
+    return CORNELIS_OK;
+}
+
+int cornelis_cuda_bsdf_sample(cornelis_cuda_scene *s, size_t n, const int32_t *mat, const float *wo, const float *N,
+                              const float *x, float *wi, float *pdf, float *f) {
+    if (int rc = checkScene(s))
+        return rc;
+    if (!mat || !wo || !N || !x || !wi || !pdf || !f)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "null argument");
+    if (n == 0)
+        return CORNELIS_OK;
+    if (int rc = checkMaterialIds(s, n, mat))
+        return rc;
+    UPLOAD(s->stageI[0], mat, n);
+    UPLOAD(s->stageF[0], wo, 3 * n);
+    UPLOAD(s->stageF[1], N, 3 * n);
+    UPLOAD(s->stageF[2], x, 3 * n);
+    CB_CUDA(s->stageF[3].reserve(3 * n));
+    CB_CUDA(s->stageF[4].reserve(n));
+    CB_CUDA(s->stageF[5].reserve(3 * n));
+    launchBsdfSample(s->stream, s->shape, s->materials.ptr, static_cast<uint32_t>(n), s->stageI[0].ptr, s->stageF[0].ptr,
+                     s->stageF[1].ptr, s->stageF[2].ptr, s->stageF[3].ptr, s->stageF[4].ptr, s->stageF[5].ptr);
+    DOWNLOAD(wi, s->stageF[3], 3 * n);
+    DOWNLOAD(pdf, s->stageF[4], n);
+    DOWNLOAD(f, s->stageF[5], 3 * n);
+    CB_CUDA(cudaStreamSynchronize(s->stream));
+    CB_CUDA(cudaGetLastError());
+    return CORNELIS_OK;
+}
+
+int cornelis_cuda_bsdf_eval(cornelis_cuda_scene *s, size_t n, const int32_t *mat, const float *wi, const float *wo,
+                            const float *N, float *f, float *pdf) {
+    if (int rc = checkScene(s))
+        return rc;
+    if (!mat || !wi || !wo || !N || !f || !pdf)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "null argument");
+    if (n == 0)
+        return CORNELIS_OK;
+    if (int rc = checkMaterialIds(s, n, mat))
+        return rc;
+    UPLOAD(s->stageI[0], mat, n);
+    UPLOAD(s->stageF[0], wi, 3 * n);
+    UPLOAD(s->stageF[1], wo, 3 * n);
+    UPLOAD(s->stageF[2], N, 3 * n);
+    CB_CUDA(s->stageF[3].reserve(3 * n));
+    CB_CUDA(s->stageF[4].reserve(n));
+    launchBsdfEval(s->stream, s->shape, s->materials.ptr, static_cast<uint32_t>(n), s->stageI[0].ptr, s->stageF[0].ptr,
+                   s->stageF[1].ptr, s->stageF[2].ptr, s->stageF[3].ptr, s->stageF[4].ptr);
+    DOWNLOAD(f, s->stageF[3], 3 * n);
+    DOWNLOAD(pdf, s->stageF[4], n);
+    CB_CUDA(cudaStreamSynchronize(s->stream));
+    CB_CUDA(cudaGetLastError());
+    return CORNELIS_OK;
+}
+
+int cornelis_cuda_shade(cornelis_cuda_scene *s, size_t n, int32_t depth, const float *u, const float *P, const float *N,
+                        const int32_t *mat, float *org, float *dir, float *thr, float *rad, uint8_t *alive) {
+    if (int rc = checkScene(s))
+        return rc;
+    if (!u || !P || !N || !mat || !org || !dir || !thr || !rad || !alive || depth < 0)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "null argument");
+    if (n == 0)
+        return CORNELIS_OK;
+    if (int rc = checkMaterialIds(s, n, mat))
+        return rc;
+    UPLOAD(s->stageI[0], mat, n);
+    UPLOAD(s->stageF[0], u, 4 * n);
+    UPLOAD(s->stageF[1], P, 3 * n);
+    UPLOAD(s->stageF[2], N, 3 * n);
+    UPLOAD(s->stageF[3], org, 3 * n);
+    UPLOAD(s->stageF[4], dir, 3 * n);
+    UPLOAD(s->stageF[5], thr, 3 * n);
+    UPLOAD(s->stageF[6], rad, 3 * n);
+    CB_CUDA(s->outRgb8.reserve(n));
+    launchShadeExplicit(s->stream, s->shape, s->materials.ptr, static_cast<uint32_t>(n), static_cast<uint32_t>(depth),
+                        s->stageF[0].ptr, s->stageF[1].ptr, s->stageF[2].ptr, s->stageI[0].ptr, s->stageF[3].ptr,
+                        s->stageF[4].ptr, s->stageF[5].ptr, s->stageF[6].ptr, s->outRgb8.ptr);
+    DOWNLOAD(org, s->stageF[3], 3 * n);
+    DOWNLOAD(dir, s->stageF[4], 3 * n);
+    DOWNLOAD(thr, s->stageF[5], 3 * n);
+    DOWNLOAD(rad, s->stageF[6], 3 * n);
+    DOWNLOAD(alive, s->outRgb8, n);
+    CB_CUDA(cudaStreamSynchronize(s->stream));
+    CB_CUDA(cudaGetLastError());
+    return CORNELIS_OK;
+}
+
+int cornelis_cuda_rng_uniforms(cornelis_cuda_scene *s, uint64_t seed, size_t n, const uint32_t *pixel,
+                               const uint32_t *sample, const uint32_t *block, float *out) {
+    if (int rc = checkScene(s))
+        return rc;
+    if (!pixel || !sample || !block || !out)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "null argument");
+    if (n == 0)
+        return CORNELIS_OK;
+    DeviceBuffer<int32_t> &a = s->stageI[0], &b = s->stageI[1], &c = s->stageI[2];
+    CB_CUDA(a.reserve(n));
+    CB_CUDA(b.reserve(n));
+    CB_CUDA(c.reserve(n));
+    CB_CUDA(cudaMemcpyAsync(a.ptr, pixel, n * 4, cudaMemcpyHostToDevice, s->stream));
+    CB_CUDA(cudaMemcpyAsync(b.ptr, sample, n * 4, cudaMemcpyHostToDevice, s->stream));
+    CB_CUDA(cudaMemcpyAsync(c.ptr, block, n * 4, cudaMemcpyHostToDevice, s->stream));
+    CB_CUDA(s->stageF[0].reserve(4 * n));
+    launchRng(s->stream, s->shape, static_cast<uint32_t>(n), static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32),
+              reinterpret_cast<const uint32_t *>(a.ptr), reinterpret_cast<const uint32_t *>(b.ptr),
+              reinterpret_cast<const uint32_t *>(c.ptr), s->stageF[0].ptr);
+    DOWNLOAD(out, s->stageF[0], 4 * n);
+    CB_CUDA(cudaStreamSynchronize(s->stream));
+    CB_CUDA(cudaGetLastError());
+    return CORNELIS_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,101 @@
+// Device-side data layout of the render path (shared by host upload code and kernels).
+//
+// Everything a kernel reads per ray lives in float4 arrays so that a warp's accesses are 16-byte vector loads of
+// consecutive addresses (the reference's SoA vectors, include/cornelis/SoA.hpp:144-176 and src/Render.cpp:47-61,
+// regrouped four floats at a time).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace cornelis_b200 {
+
+// Scene tables.  Built on the host with the reference's own arithmetic (api.cu) and staged into shared memory by
+// every kernel that intersects or shades.
+struct DevSphere {   // float4
+    float cx, cy, cz; // center (Scene.cpp:12-14)
+    float r2;         // sphereRadius * sphereRadius, the only form Geometry.cpp:81 uses
+};
+
+struct DevPlane {    // 4 x float4
+    float px, py, pz, width;   // point on the plane; extents[0] (Scene.cpp:28-33)
+    float nx, ny, nz, height;  // normal;             extents[1]
+    float tx, ty, tz; uint32_t material; // constructBasis(normal).T (Math.hpp:424-434), hoisted out of Geometry.cpp:165
+    float bx, by, bz; uint32_t pad;      // constructBasis(normal).B
+};
+
+struct DevMaterial { // 4 x float4 — StandardMaterial (Materials.hpp:325-338) with its constants folded
+    float er, eg, eb, on_a;        // emission; OrenNayarBRDF::a_ (Materials.hpp:208)
+    float dr, dg, db, on_b;        // albedo / Pi (Materials.hpp:226, Color.cpp:11-17); OrenNayarBRDF::b_
+    float tr, tg, tb, alpha;       // glossy tint; GlossyBRDF::alpha_ = roughness^2 (Materials.hpp:296-299)
+    float ior, r0, gtr_a, alpha2;  // refidx; Schlick R0 for (1, ior) (Materials.cpp:39-40); alpha2/(2 Pi); alpha^2
+};
+
+struct DevCamera {   // PerspectiveCamera (Camera.hpp:57-60), produced by lookAt (Camera.cpp:15-34)
+    float ex, ey, ez, pad0;
+    float cx, cy, cz, pad1; // corner_
+    float ux, uy, uz, pad2;
+    float vx, vy, vz, pad3;
+};
+
+struct SceneView {
+    const DevSphere *spheres;
+    const uint32_t *sphereMaterial;
+    const DevPlane *planes;
+    const DevMaterial *materials;
+    uint32_t nSpheres, nPlanes, nMaterials, pad;
+    DevCamera camera;
+};
+
+// Path pool: four float4 arrays — 64 B per path.
+//   org  = ray origin xyz | unused
+//   dir  = ray direction xyz | unused
+//   thr  = path throughput rgb | pixel index (uint bits)         (PathThroughputTag, Render.cpp:39-41)
+//   rad  = radiance collected so far rgb | sample << 8 | depth   (LightInTag, Render.cpp:43-45)
+struct PathPool {
+    float4 *org, *dir, *thr, *rad;
+};
+
+// Hit record: t and the primitive that produced it (sphere index, or nSpheres + plane index, or -1).
+// P, N and the material id are re-derived in the shade kernel with the reference's expressions.
+struct __align__(8) HitRecord {
+    float t;
+    int32_t prim;
+};
+
+// Terminated path with non-zero radiance, waiting for the accumulate kernel.
+struct __align__(16) FinishedPath {
+    float r, g, b;
+    uint32_t pixel;
+};
+
+// Device-resident bookkeeping of the wavefront; one instance per scene handle.
+struct Control {
+    uint32_t nIn;       // rays in the current pool (survivors of the last pass + regenerated camera paths)
+    uint32_t nSurvive;  // survivors appended to the next pool by shade
+    uint32_t nHit;      // entries in the hit queue (compaction #1)
+    uint32_t nFinished; // entries in the finished queue
+    uint32_t genBase;   // raygen plan: first free slot
+    uint32_t genCount;  //              number of camera paths to start this pass
+    uint32_t maxDepth;  // deepest bounce seen
+    uint32_t pad;
+    unsigned long long cursor;     // next camera path (0 .. total)
+    unsigned long long total;      // npixels * sample_count
+    unsigned long long genFirst;   // raygen plan: first camera path index of this pass
+    unsigned long long rays;       // rays intersected
+    unsigned long long shaded;     // hits shaded
+    unsigned long long iterations; // passes
+};
+
+struct RenderConfig {
+    uint32_t width, height, npixels;
+    uint32_t firstSample;
+    uint32_t maxDepth;  // 0 = unlimited
+    uint32_t poolPaths;
+    uint32_t variance;  // accumulate second moments
+    uint32_t pad;
+    uint32_t key0, key1; // Philox key = seed
+    float dx, dy;       // 1.0f / width, 1.0f / height (Render.cpp:31)
+};
+
+} // namespace cornelis_b200

@@ -1,0 +1,167 @@
+// sm_100a kernels of the wavefront render loop.
+//
+//   plan        1 thread: sizes the pass (how many camera paths to regenerate), resets the queue tails
+//   raygen      generateCameraRays            (reference src/Render.cpp:85-100)            HBM-write bound
+//   intersect   intersect + compaction #1     (Render.cpp:110-150, Geometry.cpp:34-178)    FP32-pipe bound
+//   shade       accumulateAndBounce + compaction #2 (Render.cpp:167-218, Materials.*)      FP32/SFU-pipe bound
+//   accumulate  per-pixel sum of finished paths (Render.cpp:245-248)                       HBM (atomics) bound
+//   resolve     color * (1/spp), optional display transform (Render.cpp:250, 257-261)      HBM bound
+//
+// A "pass" runs all live paths one bounce forward.  Paths that end (miss, Russian roulette, depth cap) are replaced
+// by fresh camera paths at the start of the next pass, so every pass works on a full pool until the sample budget
+// is exhausted; the reference instead drains one pixel's samples at a time (Render.cpp:232-243).
+//
+// All kernels are persistent grid-stride loops (grid = a multiple of the SM count) that read their trip counts from
+// the device-resident Control block, so the host never synchronises inside a batch of passes.
+#pragma once
+
+#include "device_types.h"
+#include "geometry.cuh"
+#include "materials.cuh"
+#include "math.cuh"
+#include "rng.cuh"
+
+namespace cornelis_b200 {
+
+constexpr int kBlockThreads = 256;
+constexpr int kWarpsPerBlock = kBlockThreads / 32;
+
+// --------------------------------------------------------------------------------------------- shared scene --
+
+// Scene tables staged in dynamic shared memory: [spheres][planes][materials][sphere material ids].
+struct SharedScene {
+    const DevSphere *spheres;
+    const DevPlane *planes;
+    const DevMaterial *materials;
+    const uint32_t *sphereMaterial;
+};
+
+__host__ __device__ inline size_t sharedSceneBytes(uint32_t nSpheres, uint32_t nPlanes, uint32_t nMaterials) {
+    return sizeof(DevSphere) * nSpheres + sizeof(DevPlane) * nPlanes + sizeof(DevMaterial) * nMaterials +
+           sizeof(uint32_t) * nSpheres;
+}
+
+// Cooperative 16-byte copies global -> shared; every table is a multiple of 16 bytes except the id list.
+__device__ __forceinline__ SharedScene stageScene(const SceneView &scene, unsigned char *smem, bool wantMaterials) {
+    float4 *dst = reinterpret_cast<float4 *>(smem);
+    uint32_t const nS4 = scene.nSpheres;                          // 1 float4 per sphere
+    uint32_t const nP4 = scene.nPlanes * 4;                       // 4 float4 per plane
+    uint32_t const nM4 = wantMaterials ? scene.nMaterials * 4 : 0; // 4 float4 per material
+    const float4 *srcS = reinterpret_cast<const float4 *>(scene.spheres);
+    const float4 *srcP = reinterpret_cast<const float4 *>(scene.planes);
+    const float4 *srcM = reinterpret_cast<const float4 *>(scene.materials);
+    for (uint32_t k = threadIdx.x; k < nS4; k += blockDim.x)
+        dst[k] = srcS[k];
+    for (uint32_t k = threadIdx.x; k < nP4; k += blockDim.x)
+        dst[nS4 + k] = srcP[k];
+    for (uint32_t k = threadIdx.x; k < nM4; k += blockDim.x)
+        dst[nS4 + nP4 + k] = srcM[k];
+    uint32_t *ids = reinterpret_cast<uint32_t *>(dst + nS4 + nP4 + scene.nMaterials * 4);
+    if (wantMaterials)
+        for (uint32_t k = threadIdx.x; k < scene.nSpheres; k += blockDim.x)
+            ids[k] = scene.sphereMaterial[k];
+    __syncthreads();
+    SharedScene s;
+    s.spheres = reinterpret_cast<const DevSphere *>(dst);
+    s.planes = reinterpret_cast<const DevPlane *>(dst + nS4);
+    s.materials = reinterpret_cast<const DevMaterial *>(dst + nS4 + nP4);
+    s.sphereMaterial = ids;
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------ compaction --
+
+// Active-path compaction (the reference's order-preserving list rebuilds, Render.cpp:142-149 and :215-217) as an
+// unordered stream append: warp ballot + popc prefix inside each warp, a 8-entry shared scan across the block's
+// warps, ONE atomicAdd per block per queue on the device-side tail.  Two queues are served per call so that the
+// two __syncthreads are shared.  Order need not be preserved: a path's random numbers are keyed by
+// (pixel, sample, depth), not by its position in a list.
+struct AppendSlots {
+    uint32_t a, b; // destination index in queue A / queue B (valid where the flag was set)
+};
+
+__device__ __forceinline__ AppendSlots blockAppend2(bool flagA, bool flagB, uint32_t *tailA, uint32_t *tailB,
+                                                    uint32_t (*scratch)[kWarpsPerBlock + 1]) {
+    unsigned const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned const maskA = __ballot_sync(0xffffffffu, flagA);
+    unsigned const maskB = __ballot_sync(0xffffffffu, flagB);
+    unsigned const below = (1u << lane) - 1u;
+    if (lane == 0) {
+        scratch[0][warp] = __popc(maskA);
+        scratch[1][warp] = __popc(maskB);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) { // thread 0 scans queue A, thread 1 queue B
+        uint32_t running = 0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerBlock; w++) {
+            uint32_t c = scratch[threadIdx.x][w];
+            scratch[threadIdx.x][w] = running;
+            running += c;
+        }
+        uint32_t base = 0;
+        if (running)
+            base = atomicAdd(threadIdx.x == 0 ? tailA : tailB, running);
+        scratch[threadIdx.x][kWarpsPerBlock] = base;
+    }
+    __syncthreads();
+    AppendSlots s;
+    s.a = scratch[0][kWarpsPerBlock] + scratch[0][warp] + __popc(maskA & below);
+    s.b = scratch[1][kWarpsPerBlock] + scratch[1][warp] + __popc(maskB & below);
+    __syncthreads(); // scratch is reused by the next grid-stride step
+    return s;
+}
+
+// ----------------------------------------------------------------------------------------------- path packing --
+
+__device__ __forceinline__ uint32_t packSampleDepth(uint32_t sample, uint32_t depth) {
+    return (sample << 8) | (depth > 255u ? 255u : depth);
+}
+
+// -------------------------------------------------------------------------------------------------- raygen --
+
+// PerspectiveCamera::operator() (Camera.cpp:11-13): (corner + x*u + y*v).normalize(), where nanovdb's normalize
+// multiplies by the rounded reciprocal of the length without any small-length guard (NanoVDB.h:919-953).
+CB_HD V3 cameraDirection(const DevCamera &c, float x, float y) {
+    V3 xu{x * c.ux, x * c.uy, x * c.uz};
+    V3 yv{y * c.vx, y * c.vy, y * c.vz};
+    V3 d = (V3{c.cx, c.cy, c.cz} + xu) + yv;
+    float s = 1.0f / sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+    return V3{d.x * s, d.y * s, d.z * s};
+}
+
+// NormalizedFrameBufferCoord + the jittered film position of Render.cpp:29-37, 96.
+CB_HD V3 pixelRayDirection(const DevCamera &c, uint32_t i, uint32_t j, float dx, float dy, float phi1, float phi2) {
+    float x = static_cast<float>(i) * dx;
+    float y = static_cast<float>(j) * dy;
+    return cameraDirection(c, x + phi1 * dx, y + phi2 * dy);
+}
+
+// ----------------------------------------------------------------------------------------------- shade body --
+
+// accumulateAndBounce for one ray (Render.cpp:173-216).  u = (RR draw, x0, x1, x2).
+// Returns true if the path survives; org/dir/thr are then the next ray and the updated throughput.
+__device__ __forceinline__ bool shadeBounce(const DevMaterial &mat, V3 P, V3 N, uint32_t depth, float u0, float x0,
+                                            float x1, float x2, V3 &org, V3 &dir, RGBf &thr, RGBf &rad) {
+    V3 const wOut = -dir;                                                   // Render.cpp:174
+    float const prob = russianRouletteFactor(thr.r, thr.g, thr.b, depth);   // Render.cpp:182
+    rad.r += thr.r * mat.er;                                                // Render.cpp:187, :67-69
+    rad.g += thr.g * mat.eg;
+    rad.b += thr.b * mat.eb;
+    if (prob < u0)                                                          // Render.cpp:189
+        return false;
+    Basis const basis = constructBasis(N);                                  // Render.cpp:194
+    V3 wIn;
+    float pdf;
+    RGBf const f = layeredSample(mat, wOut, x0, x1, x2, basis, wIn, pdf);   // Render.cpp:200
+    org = P + wIn * 0.0001f;                                                // Render.cpp:207
+    dir = wIn;                                                              // Render.cpp:208
+    float const c = fabsf(dot(wIn, N));
+    float const denom = pdf * prob;
+    thr.r *= (f.r * c) / denom;                                             // Render.cpp:210-213, Color.cpp:11-17
+    thr.g *= (f.g * c) / denom;
+    thr.b *= (f.b * c) / denom;
+    return true;
+}
+
+} // namespace cornelis_b200

@@ -1,0 +1,72 @@
+// FP32 recipes of the reference's Math.hpp, written once for host and device.
+//
+// Operation ORDER matters here: the intersection kernel has to reproduce the reference's t bit for bit, so every
+// expression keeps the reference's association (dot = a0*b0 + a1*b1 + a2*b2 left to right, Math.hpp:278) and the
+// translation unit is compiled with --fmad=false (no contraction), IEEE division and square root.
+#pragma once
+
+#include <cmath>
+#include <cuda_runtime.h>
+
+#define CB_HD __host__ __device__ __forceinline__
+
+namespace cornelis_b200 {
+
+struct V3 {
+    float x, y, z;
+};
+
+constexpr float kRayEpsilon = 0.00005f;   // Math.hpp:20
+constexpr float kPi = 3.14159265359f;     // Math.hpp:25
+
+CB_HD bool isAlmostZero(float v) { return fabsf(v) < kRayEpsilon; } // Math.hpp:22
+
+// std::max / std::min / std::clamp semantics — NOT fmaxf/fminf: with a NaN second argument std::max returns the
+// first (Materials.hpp:223-227 relies on std::max(0.0f, NaN) == 0).
+CB_HD float stdMax(float a, float b) { return (a < b) ? b : a; }
+CB_HD float stdMin(float a, float b) { return (b < a) ? b : a; }
+CB_HD float stdClamp(float v, float lo, float hi) { return (v < lo) ? lo : (hi < v) ? hi : v; }
+
+CB_HD V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+CB_HD V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }   // Math.hpp:63-70
+CB_HD V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }   // Math.hpp:75-82
+CB_HD V3 operator-(V3 a) { return V3{-a.x, -a.y, -a.z}; }                        // Math.hpp:86-93
+CB_HD V3 operator*(V3 a, V3 b) { return V3{a.x * b.x, a.y * b.y, a.z * b.z}; }   // Math.hpp:98-105
+CB_HD V3 operator*(V3 a, float s) { return V3{a.x * s, a.y * s, a.z * s}; }      // Math.hpp:110-117
+CB_HD V3 operator*(float s, V3 a) { return V3{s * a.x, s * a.y, s * a.z}; }      // Math.hpp:121-128
+CB_HD float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }        // Math.hpp:278
+CB_HD float mag2(V3 a) { return dot(a, a); }                                     // Math.hpp:284
+CB_HD V3 rayT(V3 o, V3 d, float t) { return o + d * V3{t, t, t}; }               // Math.hpp:290-292
+
+CB_HD V3 cross(V3 a, V3 b) { // Math.hpp:380-384
+    return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+
+// Math.hpp:392-398: length below RayEpsilon collapses to the zero vector; otherwise multiply by the ROUNDED
+// reciprocal (not a division per component).
+CB_HD V3 normalize(V3 v) {
+    float len = sqrtf(mag2(v));
+    if (isAlmostZero(len))
+        return V3{0.0f, 0.0f, 0.0f};
+    float s = 1.0f / len;
+    return v * V3{s, s, s};
+}
+
+struct Basis {
+    V3 N, T, B;
+};
+
+// Math.hpp:424-434.  `abs(N(1)) > 0.95` compares a float against a double literal; the smallest float above
+// 0.95 is also the smallest float above 0.95f, so the float comparison below decides identically.
+CB_HD Basis constructBasis(V3 N) {
+    V3 helper{0.0f, 1.0f, 0.0f};
+    if (fabsf(N.y) > 0.95f)
+        helper = V3{0.0f, 0.0f, 1.0f};
+    Basis b;
+    b.N = N;
+    b.T = normalize(cross(helper, N));
+    b.B = cross(b.T, N);
+    return b;
+}
+
+} // namespace cornelis_b200

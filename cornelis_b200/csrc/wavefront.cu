@@ -1,0 +1,471 @@
+// Wavefront kernels (see kernels.cuh for the pipeline overview) and their launchers.
+#include "kernels.cuh"
+#include "wavefront.h"
+
+namespace cornelis_b200 {
+
+// ---------------------------------------------------------------------------------------------------- plan --
+
+// One thread.  Turns the survivors of the previous pass into the head of the new pool and decides how many camera
+// paths to regenerate behind them.
+__global__ void k_plan(Control *ctl, RenderConfig cfg) {
+    uint32_t const survivors = ctl->nSurvive;
+    unsigned long long const remaining = ctl->total - ctl->cursor;
+    uint32_t const room = cfg.poolPaths - survivors;
+    uint32_t const gen = remaining < room ? static_cast<uint32_t>(remaining) : room;
+    ctl->genBase = survivors;
+    ctl->genCount = gen;
+    ctl->genFirst = ctl->cursor;
+    ctl->cursor += gen;
+    ctl->nIn = survivors + gen;
+    ctl->nSurvive = 0;
+    ctl->nHit = 0;
+    ctl->nFinished = 0;
+    ctl->rays += survivors + gen;
+    ctl->iterations += (survivors + gen) ? 1 : 0;
+}
+
+// -------------------------------------------------------------------------------------------------- raygen --
+
+// generateCameraRays (Render.cpp:85-100) for camera paths [genFirst, genFirst + genCount), written behind the
+// survivors.  Path p = sampleLocal * npixels + pixel: consecutive threads take consecutive pixels of one sample
+// index, so a warp's rays are coherent and its later framebuffer atomics hit distinct pixels.
+__global__ void __launch_bounds__(kBlockThreads) k_raygen(const Control *ctl, RenderConfig cfg, DevCamera cam,
+                                                          PathPool pool) {
+    uint32_t const count = ctl->genCount;
+    uint32_t const base = ctl->genBase;
+    unsigned long long const first = ctl->genFirst;
+    uint32_t const sample0 = static_cast<uint32_t>(first / cfg.npixels);
+    uint32_t const pixel0 = static_cast<uint32_t>(first % cfg.npixels);
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+        uint32_t pixel = pixel0 + k; // < npixels + poolPaths, no overflow
+        uint32_t const wraps = pixel / cfg.npixels;
+        pixel -= wraps * cfg.npixels;
+        uint32_t const sample = cfg.firstSample + sample0 + wraps;
+        uint32_t const j = pixel / cfg.width, i = pixel - j * cfg.width;
+        Philox4 const r = philox4x32_10(pixel, sample, 0u, 0u, cfg.key0, cfg.key1);
+        float const phi1 = uniformFromBits(r.v[0]), phi2 = uniformFromBits(r.v[1]); // Render.cpp:94-95
+        V3 const d = pixelRayDirection(cam, i, j, cfg.dx, cfg.dy, phi1, phi2);
+        uint32_t const slot = base + k;
+        pool.org[slot] = make_float4(cam.ex, cam.ey, cam.ez, 0.0f);
+        pool.dir[slot] = make_float4(d.x, d.y, d.z, 0.0f);
+        pool.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(packSampleDepth(sample, 0))); // Render.cpp:58
+        pool.rad[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(pixel));                     // Render.cpp:60
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ intersect --
+
+// intersect (Render.cpp:110-150): closest hit of every pooled ray against all spheres then all planes held in
+// shared memory, then compaction #1: hits are appended to the hit queue; misses end the path — if it carries
+// radiance it goes to the finished queue, otherwise it simply disappears.
+__global__ void __launch_bounds__(kBlockThreads) k_intersect(Control *ctl, SceneView scene, PathPool pool,
+                                                             HitRecord *__restrict__ hits,
+                                                             uint32_t *__restrict__ hitQueue,
+                                                             FinishedPath *__restrict__ finished) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint32_t scratch[2][kWarpsPerBlock + 1];
+    SharedScene const sh = stageScene(scene, smem, false);
+    uint32_t const n = ctl->nIn;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        uint32_t const i = base + threadIdx.x;
+        bool const valid = i < n;
+        bool hit = false, finish = false;
+        float4 radiance = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+            float4 const o4 = pool.org[i], d4 = pool.dir[i];
+            float t = INFINITY; // IntersectionData::reset, Geometry.cpp:7-12
+            int32_t prim = -1;
+            closestHit(V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, sh.spheres, scene.nSpheres, sh.planes,
+                       scene.nPlanes, t, prim);
+            hit = t < INFINITY; // Render.cpp:146
+            hits[i] = HitRecord{t, prim};
+            if (!hit) {
+                radiance = pool.rad[i];
+                finish = radiance.x != 0.0f || radiance.y != 0.0f || radiance.z != 0.0f;
+            }
+        }
+        AppendSlots const slot = blockAppend2(hit, finish, &ctl->nHit, &ctl->nFinished, scratch);
+        if (hit)
+            hitQueue[slot.a] = i;
+        if (finish)
+            finished[slot.b] = FinishedPath{radiance.x, radiance.y, radiance.z, __float_as_uint(radiance.w)};
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- shade --
+
+// accumulateAndBounce (Render.cpp:167-218) over the hit queue, then compaction #2: survivors are written
+// CONTIGUOUSLY into the next pool (so the next pass reads coalesced float4 streams); paths killed by Russian
+// roulette or the depth cap go to the finished queue if they carry radiance.
+__global__ void __launch_bounds__(kBlockThreads) k_shade(Control *ctl, RenderConfig cfg, SceneView scene,
+                                                         PathPool in, PathPool out,
+                                                         const HitRecord *__restrict__ hits,
+                                                         const uint32_t *__restrict__ hitQueue,
+                                                         FinishedPath *__restrict__ finished) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint32_t scratch[2][kWarpsPerBlock + 1];
+    SharedScene const sh = stageScene(scene, smem, true);
+    uint32_t const n = ctl->nHit;
+    uint32_t deepest = 0;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        uint32_t const q = base + threadIdx.x;
+        bool const valid = q < n;
+        bool alive = false, finish = false;
+        V3 org{}, dir{};
+        RGBf thr{}, rad{};
+        uint32_t pixel = 0, sample = 0, depth = 0;
+        if (valid) {
+            uint32_t const i = hitQueue[q];
+            float4 const o4 = in.org[i], d4 = in.dir[i], t4 = in.thr[i], r4 = in.rad[i];
+            HitRecord const h = hits[i];
+            org = V3{o4.x, o4.y, o4.z};
+            dir = V3{d4.x, d4.y, d4.z};
+            thr = RGBf{t4.x, t4.y, t4.z};
+            rad = RGBf{r4.x, r4.y, r4.z};
+            uint32_t const sd = __float_as_uint(t4.w);
+            sample = sd >> 8;
+            depth = sd & 255u;
+            pixel = __float_as_uint(r4.w);
+            V3 P, N;
+            uint32_t material;
+            hitSurface(org, dir, h.t, h.prim, sh.spheres, sh.sphereMaterial, scene.nSpheres, sh.planes, P, N, material);
+            Philox4 const r = philox4x32_10(pixel, sample, depth + 1u, 0u, cfg.key0, cfg.key1);
+            alive = shadeBounce(sh.materials[material], P, N, depth, uniformFromBits(r.v[0]), uniformFromBits(r.v[1]),
+                                uniformFromBits(r.v[2]), uniformFromBits(r.v[3]), org, dir, thr, rad);
+            depth += 1;
+            deepest = depth > deepest ? depth : deepest;
+            if (cfg.maxDepth && depth >= cfg.maxDepth)
+                alive = false;
+            finish = !alive && (rad.r != 0.0f || rad.g != 0.0f || rad.b != 0.0f);
+        }
+        AppendSlots const slot = blockAppend2(alive, finish, &ctl->nSurvive, &ctl->nFinished, scratch);
+        if (alive) {
+            out.org[slot.a] = make_float4(org.x, org.y, org.z, 0.0f);
+            out.dir[slot.a] = make_float4(dir.x, dir.y, dir.z, 0.0f);
+            out.thr[slot.a] = make_float4(thr.r, thr.g, thr.b, __uint_as_float(packSampleDepth(sample, depth)));
+            out.rad[slot.a] = make_float4(rad.r, rad.g, rad.b, __uint_as_float(pixel));
+        }
+        if (finish)
+            finished[slot.b] = FinishedPath{rad.r, rad.g, rad.b, pixel};
+    }
+    // statistics: one atomic per block
+    deepest = __reduce_max_sync(0xffffffffu, deepest);
+    if ((threadIdx.x & 31u) == 0 && deepest)
+        atomicMax(&ctl->maxDepth, deepest);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&ctl->shaded, static_cast<unsigned long long>(n));
+}
+
+// ----------------------------------------------------------------------------------------------- accumulate --
+
+// Per-pixel accumulation (Render.cpp:245-248): every finished path adds its radiance to its pixel's running sum
+// with one 128-bit vector reduction (red.global.add.v4.f32); .w counts contributing paths.  With the variance
+// option the squares go to a second float4 image.
+__global__ void __launch_bounds__(kBlockThreads) k_accumulate(const Control *ctl,
+                                                              const FinishedPath *__restrict__ finished,
+                                                              float4 *__restrict__ accum, float4 *__restrict__ accum2,
+                                                              bool dropNonFinite) {
+    uint32_t const n = ctl->nFinished;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        FinishedPath const f = finished[q];
+        if (dropNonFinite && !(isfinite(f.r) && isfinite(f.g) && isfinite(f.b)))
+            continue;
+        atomicAdd(&accum[f.pixel], make_float4(f.r, f.g, f.b, 1.0f));
+        if (accum2)
+            atomicAdd(&accum2[f.pixel], make_float4(f.r * f.r, f.g * f.g, f.b * f.b, 0.0f));
+    }
+}
+
+// -------------------------------------------------------------------------------------------------- resolve --
+
+// color = sum * (1.0f / samplesAA) (Render.cpp:250) into packed RGB (FrameBuffer.hpp:66, Color.hpp:56);
+// optionally the unbiased per-sample variance from the second moments.
+__global__ void __launch_bounds__(kBlockThreads) k_resolve(uint32_t npixels, float invSamples, uint32_t samples,
+                                                           const float4 *__restrict__ accum,
+                                                           const float4 *__restrict__ accum2, float *__restrict__ rgb,
+                                                           float *__restrict__ variance) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < npixels; p += gridDim.x * blockDim.x) {
+        float4 const s = accum[p];
+        rgb[3 * p + 0] = s.x * invSamples;
+        rgb[3 * p + 1] = s.y * invSamples;
+        rgb[3 * p + 2] = s.z * invSamples;
+        if (variance) {
+            float4 const q = accum2[p];
+            double const n = samples;
+            double const sx[3] = {s.x, s.y, s.z}, sq[3] = {q.x, q.y, q.z};
+            for (int c = 0; c < 3; c++) {
+                double v = samples > 1 ? (sq[c] - sx[c] * sx[c] / n) / (n - 1.0) : 0.0;
+                variance[3 * p + c] = static_cast<float>(v > 0.0 ? v : 0.0);
+            }
+        }
+    }
+}
+
+// toSRGB (Color.cpp:64-80: 12.95 slope, double pow) + quantizeTo8bit (FrameBuffer.hpp:91-95) fused with the resolve
+// — what saveImage (Render.cpp:257-261) does on the CPU before PNG encoding.
+__device__ __forceinline__ uint8_t srgb8(float x) {
+    float s;
+    if (static_cast<double>(x) <= 0.0031308)
+        s = x * 12.95f;
+    else
+        s = static_cast<float>((1 + 0.055f) * pow(static_cast<double>(x), static_cast<double>(1.0f / 2.4f)) - 0.055f);
+    double v = round(255.0 * static_cast<double>(s));
+    v = (v < 0.0) ? 0.0 : (255.0 < v) ? 255.0 : v;
+    return static_cast<uint8_t>(v);
+}
+
+__global__ void __launch_bounds__(kBlockThreads) k_resolve_srgb8(uint32_t npixels, float invSamples,
+                                                                 const float4 *__restrict__ accum,
+                                                                 uint8_t *__restrict__ rgb8) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < npixels; p += gridDim.x * blockDim.x) {
+        float4 const s = accum[p];
+        rgb8[3 * p + 0] = srgb8(s.x * invSamples);
+        rgb8[3 * p + 1] = srgb8(s.y * invSamples);
+        rgb8[3 * p + 2] = srgb8(s.z * invSamples);
+    }
+}
+
+// ------------------------------------------------------------------------------- stage kernels on plain arrays --
+
+__global__ void __launch_bounds__(kBlockThreads) k_pixel_rays(DevCamera cam, uint32_t n, float dx, float dy,
+                                                              const int32_t *pi, const int32_t *pj, const float *phi1,
+                                                              const float *phi2, float *org, float *dir) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        V3 const d = pixelRayDirection(cam, static_cast<uint32_t>(pi[k]), static_cast<uint32_t>(pj[k]), dx, dy,
+                                       phi1[k], phi2[k]);
+        org[3 * k] = cam.ex, org[3 * k + 1] = cam.ey, org[3 * k + 2] = cam.ez;
+        dir[3 * k] = d.x, dir[3 * k + 1] = d.y, dir[3 * k + 2] = d.z;
+    }
+}
+
+// The intersect stage on a plain float4 ray batch — the same closestHit as k_intersect without the queues.
+// Used by cornelis_cuda_intersect(_device): parity tests and the intersection microbench (config 3).
+__global__ void __launch_bounds__(kBlockThreads) k_intersect_batch(SceneView scene, size_t n,
+                                                                   const float4 *__restrict__ org,
+                                                                   const float4 *__restrict__ dir,
+                                                                   HitRecord *__restrict__ hits) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SharedScene const sh = stageScene(scene, smem, false);
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        float4 const o4 = org[i], d4 = dir[i];
+        float t = INFINITY;
+        int32_t prim = -1;
+        closestHit(V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, sh.spheres, scene.nSpheres, sh.planes, scene.nPlanes, t,
+                   prim);
+        hits[i] = HitRecord{t, prim};
+    }
+}
+
+// Expands hit records into the reference's IntersectionData fields (P, N, MaterialId; Geometry.hpp:7-15).
+__global__ void __launch_bounds__(kBlockThreads) k_hit_surface(SceneView scene, size_t n,
+                                                               const float4 *__restrict__ org,
+                                                               const float4 *__restrict__ dir,
+                                                               const HitRecord *__restrict__ hits, float *P, float *N,
+                                                               int32_t *mat) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SharedScene const sh = stageScene(scene, smem, true);
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        HitRecord const h = hits[i];
+        V3 p{0, 0, 0}, nrm{0, 0, 0};
+        uint32_t m = 0xffffffffu;
+        if (h.prim >= 0) {
+            float4 const o4 = org[i], d4 = dir[i];
+            hitSurface(V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, h.t, h.prim, sh.spheres, sh.sphereMaterial,
+                       scene.nSpheres, sh.planes, p, nrm, m);
+        }
+        if (P)
+            P[3 * i] = p.x, P[3 * i + 1] = p.y, P[3 * i + 2] = p.z;
+        if (N)
+            N[3 * i] = nrm.x, N[3 * i + 1] = nrm.y, N[3 * i + 2] = nrm.z;
+        if (mat)
+            mat[i] = static_cast<int32_t>(m);
+    }
+}
+
+__global__ void __launch_bounds__(kBlockThreads) k_bsdf_sample(const DevMaterial *materials, uint32_t n,
+                                                               const int32_t *mat, const float *wo, const float *N,
+                                                               const float *x, float *wi, float *pdf, float *f) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        Basis const b = constructBasis(V3{N[3 * k], N[3 * k + 1], N[3 * k + 2]});
+        V3 w;
+        float p;
+        RGBf const v = layeredSample(materials[mat[k]], V3{wo[3 * k], wo[3 * k + 1], wo[3 * k + 2]}, x[3 * k],
+                                     x[3 * k + 1], x[3 * k + 2], b, w, p);
+        wi[3 * k] = w.x, wi[3 * k + 1] = w.y, wi[3 * k + 2] = w.z;
+        f[3 * k] = v.r, f[3 * k + 1] = v.g, f[3 * k + 2] = v.b;
+        pdf[k] = p;
+    }
+}
+
+__global__ void __launch_bounds__(kBlockThreads) k_bsdf_eval(const DevMaterial *materials, uint32_t n,
+                                                             const int32_t *mat, const float *wi, const float *wo,
+                                                             const float *N, float *f, float *pdf) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        V3 const a{wi[3 * k], wi[3 * k + 1], wi[3 * k + 2]}, o{wo[3 * k], wo[3 * k + 1], wo[3 * k + 2]};
+        V3 const nrm{N[3 * k], N[3 * k + 1], N[3 * k + 2]};
+        DevMaterial const &m = materials[mat[k]];
+        RGBf const v = layeredEval(m, a, o, nrm);
+        f[3 * k] = v.r, f[3 * k + 1] = v.g, f[3 * k + 2] = v.b;
+        pdf[k] = layeredPdf(m, a, o, nrm);
+    }
+}
+
+__global__ void __launch_bounds__(kBlockThreads) k_shade_explicit(const DevMaterial *materials, uint32_t n,
+                                                                  uint32_t depth, const float *u, const float *P,
+                                                                  const float *N, const int32_t *mat, float *org,
+                                                                  float *dir, float *thr, float *rad, uint8_t *alive) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        V3 o{org[3 * k], org[3 * k + 1], org[3 * k + 2]}, d{dir[3 * k], dir[3 * k + 1], dir[3 * k + 2]};
+        RGBf T{thr[3 * k], thr[3 * k + 1], thr[3 * k + 2]}, L{rad[3 * k], rad[3 * k + 1], rad[3 * k + 2]};
+        bool const a = shadeBounce(materials[mat[k]], V3{P[3 * k], P[3 * k + 1], P[3 * k + 2]},
+                                   V3{N[3 * k], N[3 * k + 1], N[3 * k + 2]}, depth, u[4 * k], u[4 * k + 1],
+                                   u[4 * k + 2], u[4 * k + 3], o, d, T, L);
+        alive[k] = a ? 1 : 0;
+        org[3 * k] = o.x, org[3 * k + 1] = o.y, org[3 * k + 2] = o.z;
+        dir[3 * k] = d.x, dir[3 * k + 1] = d.y, dir[3 * k + 2] = d.z;
+        thr[3 * k] = T.r, thr[3 * k + 1] = T.g, thr[3 * k + 2] = T.b;
+        rad[3 * k] = L.r, rad[3 * k + 1] = L.g, rad[3 * k + 2] = L.b;
+    }
+}
+
+__global__ void __launch_bounds__(kBlockThreads) k_rng(uint32_t n, uint32_t key0, uint32_t key1, const uint32_t *pixel,
+                                                       const uint32_t *sample, const uint32_t *block, float *out) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        Philox4 const r = philox4x32_10(pixel[k], sample[k], block[k], 0u, key0, key1);
+        for (int c = 0; c < 4; c++)
+            out[4 * k + c] = uniformFromBits(r.v[c]);
+    }
+}
+
+// Packed xyz -> float4 staging for the host-buffer stage entry points.
+__global__ void __launch_bounds__(kBlockThreads) k_pack4(size_t n, const float *xyz, float4 *out) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        out[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0f);
+}
+
+__global__ void __launch_bounds__(kBlockThreads) k_unpack_hits(size_t n, const HitRecord *hits, float *t,
+                                                               int32_t *prim) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        t[i] = hits[i].t;
+        prim[i] = hits[i].prim;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- launchers --
+
+static inline int gridFor(size_t n, int numSMs, int blocksPerSM) {
+    size_t const want = (n + kBlockThreads - 1) / kBlockThreads;
+    size_t const cap = static_cast<size_t>(numSMs) * blocksPerSM;
+    size_t g = want < cap ? want : cap;
+    return static_cast<int>(g ? g : 1);
+}
+
+void launchPlan(cudaStream_t s, Control *ctl, const RenderConfig &cfg) { k_plan<<<1, 1, 0, s>>>(ctl, cfg); }
+
+void launchRaygen(cudaStream_t s, const LaunchShape &shape, const Control *ctl, const RenderConfig &cfg,
+                  const DevCamera &cam, const PathPool &pool) {
+    k_raygen<<<shape.gridPersistent, kBlockThreads, 0, s>>>(ctl, cfg, cam, pool);
+}
+
+void launchIntersect(cudaStream_t s, const LaunchShape &shape, Control *ctl, const SceneView &scene,
+                     const PathPool &pool, HitRecord *hits, uint32_t *hitQueue, FinishedPath *finished) {
+    k_intersect<<<shape.gridPersistent, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, scene, pool, hits, hitQueue,
+                                                                                 finished);
+}
+
+void launchShade(cudaStream_t s, const LaunchShape &shape, Control *ctl, const RenderConfig &cfg,
+                 const SceneView &scene, const PathPool &in, const PathPool &out, const HitRecord *hits,
+                 const uint32_t *hitQueue, FinishedPath *finished) {
+    k_shade<<<shape.gridPersistent, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, cfg, scene, in, out, hits, hitQueue,
+                                                                             finished);
+}
+
+void launchAccumulate(cudaStream_t s, const LaunchShape &shape, const Control *ctl, const FinishedPath *finished,
+                      float4 *accum, float4 *accum2, bool dropNonFinite) {
+    k_accumulate<<<shape.gridPersistent, kBlockThreads, 0, s>>>(ctl, finished, accum, accum2, dropNonFinite);
+}
+
+void launchResolve(cudaStream_t s, const LaunchShape &shape, uint32_t npixels, uint32_t samples, const float4 *accum,
+                   const float4 *accum2, float *rgb, float *variance) {
+    float const inv = 1.0f / static_cast<float>(static_cast<int32_t>(samples)); // 1.0f / options.samplesAA
+    k_resolve<<<gridFor(npixels, shape.numSMs, 8), kBlockThreads, 0, s>>>(npixels, inv, samples, accum, accum2, rgb,
+                                                                          variance);
+}
+
+void launchResolveSrgb8(cudaStream_t s, const LaunchShape &shape, uint32_t npixels, uint32_t samples,
+                        const float4 *accum, uint8_t *rgb8) {
+    float const inv = 1.0f / static_cast<float>(static_cast<int32_t>(samples));
+    k_resolve_srgb8<<<gridFor(npixels, shape.numSMs, 8), kBlockThreads, 0, s>>>(npixels, inv, accum, rgb8);
+}
+
+void launchPixelRays(cudaStream_t s, const LaunchShape &shape, const DevCamera &cam, uint32_t n, float dx, float dy,
+                     const int32_t *pi, const int32_t *pj, const float *phi1, const float *phi2, float *org,
+                     float *dir) {
+    k_pixel_rays<<<gridFor(n, shape.numSMs, 8), kBlockThreads, 0, s>>>(cam, n, dx, dy, pi, pj, phi1, phi2, org, dir);
+}
+
+void launchIntersectBatch(cudaStream_t s, const LaunchShape &shape, const SceneView &scene, size_t n,
+                          const float4 *org, const float4 *dir, HitRecord *hits) {
+    k_intersect_batch<<<gridFor(n, shape.numSMs, shape.blocksPerSM), kBlockThreads, shape.sceneSmemBytes, s>>>(
+        scene, n, org, dir, hits);
+}
+
+void launchHitSurface(cudaStream_t s, const LaunchShape &shape, const SceneView &scene, size_t n, const float4 *org,
+                      const float4 *dir, const HitRecord *hits, float *P, float *N, int32_t *mat) {
+    k_hit_surface<<<gridFor(n, shape.numSMs, shape.blocksPerSM), kBlockThreads, shape.sceneSmemBytes, s>>>(
+        scene, n, org, dir, hits, P, N, mat);
+}
+
+void launchBsdfSample(cudaStream_t s, const LaunchShape &shape, const DevMaterial *materials, uint32_t n,
+                      const int32_t *mat, const float *wo, const float *N, const float *x, float *wi, float *pdf,
+                      float *f) {
+    k_bsdf_sample<<<gridFor(n, shape.numSMs, 8), kBlockThreads, 0, s>>>(materials, n, mat, wo, N, x, wi, pdf, f);
+}
+
+void launchBsdfEval(cudaStream_t s, const LaunchShape &shape, const DevMaterial *materials, uint32_t n,
+                    const int32_t *mat, const float *wi, const float *wo, const float *N, float *f, float *pdf) {
+    k_bsdf_eval<<<gridFor(n, shape.numSMs, 8), kBlockThreads, 0, s>>>(materials, n, mat, wi, wo, N, f, pdf);
+}
+
+void launchShadeExplicit(cudaStream_t s, const LaunchShape &shape, const DevMaterial *materials, uint32_t n,
+                         uint32_t depth, const float *u, const float *P, const float *N, const int32_t *mat,
+                         float *org, float *dir, float *thr, float *rad, uint8_t *alive) {
+    k_shade_explicit<<<gridFor(n, shape.numSMs, 8), kBlockThreads, 0, s>>>(materials, n, depth, u, P, N, mat, org, dir,
+                                                                           thr, rad, alive);
+}
+
+void launchRng(cudaStream_t s, const LaunchShape &shape, uint32_t n, uint32_t key0, uint32_t key1,
+               const uint32_t *pixel, const uint32_t *sample, const uint32_t *block, float *out) {
+    k_rng<<<gridFor(n, shape.numSMs, 8), kBlockThreads, 0, s>>>(n, key0, key1, pixel, sample, block, out);
+}
+
+void launchPack4(cudaStream_t s, const LaunchShape &shape, size_t n, const float *xyz, float4 *out) {
+    k_pack4<<<gridFor(n, shape.numSMs, 8), kBlockThreads, 0, s>>>(n, xyz, out);
+}
+
+void launchUnpackHits(cudaStream_t s, const LaunchShape &shape, size_t n, const HitRecord *hits, float *t,
+                      int32_t *prim) {
+    k_unpack_hits<<<gridFor(n, shape.numSMs, 8), kBlockThreads, 0, s>>>(n, hits, t, prim);
+}
+
+cudaError_t configureKernels(size_t sceneSmemBytes) {
+    // Scenes whose tables exceed the default 48 KB of dynamic shared memory opt in to the large carve-out.
+    if (sceneSmemBytes <= 48 * 1024)
+        return cudaSuccess;
+    cudaError_t e;
+    int const bytes = static_cast<int>(sceneSmemBytes);
+    if ((e = cudaFuncSetAttribute(k_intersect, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
+        return e;
+    if ((e = cudaFuncSetAttribute(k_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
+        return e;
+    if ((e = cudaFuncSetAttribute(k_intersect_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
+        return e;
+    return cudaFuncSetAttribute(k_hit_surface, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+} // namespace cornelis_b200

@@ -1,0 +1,57 @@
+// Host-callable launchers for the kernels in wavefront.cu.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "device_types.h"
+
+namespace cornelis_b200 {
+
+struct LaunchShape {
+    int numSMs = 148;         // B200: 148 SMs; queried at scene creation
+    int blocksPerSM = 4;      // resident 256-thread CTAs per SM the persistent kernels are sized for
+    int gridPersistent = 592; // numSMs * blocksPerSM
+    size_t sceneSmemBytes = 0;
+};
+
+cudaError_t configureKernels(size_t sceneSmemBytes);
+
+void launchPlan(cudaStream_t s, Control *ctl, const RenderConfig &cfg);
+void launchRaygen(cudaStream_t s, const LaunchShape &shape, const Control *ctl, const RenderConfig &cfg,
+                  const DevCamera &cam, const PathPool &pool);
+void launchIntersect(cudaStream_t s, const LaunchShape &shape, Control *ctl, const SceneView &scene,
+                     const PathPool &pool, HitRecord *hits, uint32_t *hitQueue, FinishedPath *finished);
+void launchShade(cudaStream_t s, const LaunchShape &shape, Control *ctl, const RenderConfig &cfg,
+                 const SceneView &scene, const PathPool &in, const PathPool &out, const HitRecord *hits,
+                 const uint32_t *hitQueue, FinishedPath *finished);
+void launchAccumulate(cudaStream_t s, const LaunchShape &shape, const Control *ctl, const FinishedPath *finished,
+                      float4 *accum, float4 *accum2, bool dropNonFinite);
+void launchResolve(cudaStream_t s, const LaunchShape &shape, uint32_t npixels, uint32_t samples, const float4 *accum,
+                   const float4 *accum2, float *rgb, float *variance);
+void launchResolveSrgb8(cudaStream_t s, const LaunchShape &shape, uint32_t npixels, uint32_t samples,
+                        const float4 *accum, uint8_t *rgb8);
+
+void launchPixelRays(cudaStream_t s, const LaunchShape &shape, const DevCamera &cam, uint32_t n, float dx, float dy,
+                     const int32_t *pi, const int32_t *pj, const float *phi1, const float *phi2, float *org,
+                     float *dir);
+void launchIntersectBatch(cudaStream_t s, const LaunchShape &shape, const SceneView &scene, size_t n,
+                          const float4 *org, const float4 *dir, HitRecord *hits);
+void launchHitSurface(cudaStream_t s, const LaunchShape &shape, const SceneView &scene, size_t n, const float4 *org,
+                      const float4 *dir, const HitRecord *hits, float *P, float *N, int32_t *mat);
+void launchBsdfSample(cudaStream_t s, const LaunchShape &shape, const DevMaterial *materials, uint32_t n,
+                      const int32_t *mat, const float *wo, const float *N, const float *x, float *wi, float *pdf,
+                      float *f);
+void launchBsdfEval(cudaStream_t s, const LaunchShape &shape, const DevMaterial *materials, uint32_t n,
+                    const int32_t *mat, const float *wi, const float *wo, const float *N, float *f, float *pdf);
+void launchShadeExplicit(cudaStream_t s, const LaunchShape &shape, const DevMaterial *materials, uint32_t n,
+                         uint32_t depth, const float *u, const float *P, const float *N, const int32_t *mat,
+                         float *org, float *dir, float *thr, float *rad, uint8_t *alive);
+void launchRng(cudaStream_t s, const LaunchShape &shape, uint32_t n, uint32_t key0, uint32_t key1,
+               const uint32_t *pixel, const uint32_t *sample, const uint32_t *block, float *out);
+void launchPack4(cudaStream_t s, const LaunchShape &shape, size_t n, const float *xyz, float4 *out);
+void launchUnpackHits(cudaStream_t s, const LaunchShape &shape, size_t n, const HitRecord *hits, float *t,
+                      int32_t *prim);
+
+} // namespace cornelis_b200

@@ -1,0 +1,198 @@
+/* cornelis_cuda.h — C-ABI of the B200 render path.
+ *
+ * This is the drop-in boundary for the reference's batched render loop.  The reference has no FFI: the seam it
+ * replaces is the call `integrateTile(tileInfo, options, scene, fb)` that RenderSession::render makes for every
+ * tile from its TBB workers (reference src/Render.cpp:343, body :220-255), with read-only SceneData in and disjoint
+ * pixel writes into one RGBFrameBuffer out.  One cornelis_cuda_render() call produces what the whole tile loop
+ * (Render.cpp:327-354) produces: the W x H RGB framebuffer, row-major j*W+i, three packed floats per pixel
+ * (reference include/cornelis/FrameBuffer.hpp:66, Color.hpp:56).
+ *
+ * Plain C: POD structs, pointers and sizes only; no exceptions, no STL, no torch types.  Every function returns
+ * 0 on success and a non-zero cornelis_status otherwise; cornelis_cuda_last_error() gives the message for the
+ * calling thread.  There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * CORNELIS_ERR_NO_DEVICE.
+ *
+ * Ownership: a scene handle owns all device memory (scene tables, path pool, queues, framebuffer accumulators).
+ * Pointers passed in are borrowed for the duration of the call; output buffers are caller-owned.
+ * Threading: a handle may be used by one host thread at a time; different handles are independent.
+ */
+#ifndef CORNELIS_CUDA_H
+#define CORNELIS_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CORNELIS_CUDA_ABI_VERSION 1
+
+typedef enum cornelis_status {
+    CORNELIS_OK = 0,
+    CORNELIS_ERR_INVALID_ARGUMENT = 1, /* null pointer, zero-area frame, samples <= 0 (Render.cpp:310-313), bad index */
+    CORNELIS_ERR_NO_DEVICE = 2,        /* no CUDA device / driver: the product has no CPU path */
+    CORNELIS_ERR_CUDA = 3,             /* a CUDA runtime call failed; see cornelis_cuda_last_error() */
+    CORNELIS_ERR_OUT_OF_MEMORY = 4,
+    CORNELIS_ERR_ABORTED = 5           /* the progress callback asked to stop (RenderCommand::Abort, Render.hpp:10-14) */
+} cornelis_status;
+
+/* ---- scene description PODs: field-for-field the reference's SceneDescription.hpp:14-53 ---------------------- */
+
+typedef struct cornelis_camera_desc { /* PerspectiveCameraDescription, SceneDescription.hpp:45-53 */
+    float origin[3];
+    float look_at[3];
+    float aspect;         /* multiplies the VERTICAL film vector (Camera.cpp:25) */
+    float horizontal_fov; /* radians */
+} cornelis_camera_desc;
+
+typedef struct cornelis_material_desc { /* MaterialDescription, SceneDescription.hpp:14-22 */
+    float albedo[3];
+    float emissive[3];
+    float roughness;
+    float reflection_tint[3];
+    float ior;
+} cornelis_material_desc;
+
+typedef struct cornelis_sphere_desc { /* SphereDescription, SceneDescription.hpp:30-35 */
+    float center[3];
+    float radius;
+    int32_t material; /* index into the material list; < 0 = unset -> material 0 (Scene.cpp:16) */
+} cornelis_sphere_desc;
+
+typedef struct cornelis_plane_desc { /* PlaneDescription, SceneDescription.hpp:37-43 */
+    float normal[3];
+    float point[3];
+    float extents[3]; /* [0] = width along T, [1] = height along B (Scene.cpp:33-34); [2] unused */
+    int32_t material;
+} cornelis_plane_desc;
+
+/* ---- render parameters ---------------------------------------------------------------------------------------- */
+
+enum {
+    CORNELIS_RENDER_VARIANCE = 1u << 0, /* also accumulate the per-pixel second moment (for the 3-sigma image test) */
+    CORNELIS_RENDER_KEEP = 1u << 1,     /* add to the accumulators instead of clearing them first (progressive) */
+    CORNELIS_RENDER_STAGE_TIMING = 1u << 2, /* time every stage kernel of one pass in 32 with CUDA events (stats *_ms) */
+    CORNELIS_RENDER_DROP_NONFINITE = 1u << 3 /* skip finished paths whose radiance is NaN/inf.  Off by default: the
+                                                reference lets them through (|w.z| rounding above 1 makes its
+                                                Oren-Nayar term NaN about once per 1e8 samples) */
+};
+
+enum {
+    CORNELIS_PIPELINE_DEFAULT = 0,
+    CORNELIS_PIPELINE_WAVEFRONT = 1 /* raygen -> intersect(+compact) -> shade(+compact) -> accumulate kernels */
+};
+
+typedef struct cornelis_render_params {
+    int32_t width, height;   /* the reference hard-codes 512 x 512 (Render.cpp:307) */
+    int32_t samples;         /* RenderOptions::samplesAA of the whole image: the resolve divides by it */
+    int32_t first_sample;    /* this call renders global sample indices [first_sample, first_sample + sample_count) */
+    int32_t sample_count;    /*   of every pixel — the unit of multi-GPU sharding; 0 = all `samples` */
+    int32_t max_depth;       /* <= 0: unlimited, as the reference (Render.cpp:237); else paths stop after this many bounces */
+    uint64_t seed;           /* PRNG::DefaultSeed = 19791102 (PRNG.hpp:12) */
+    uint32_t flags;          /* CORNELIS_RENDER_* */
+    int32_t pipeline;        /* CORNELIS_PIPELINE_* */
+    int32_t pool_paths;      /* paths in flight (wavefront width); 0 = default */
+    int32_t reserved;
+} cornelis_render_params;
+
+typedef struct cornelis_render_stats {
+    uint64_t pixel_samples; /* camera paths started */
+    uint64_t rays;          /* rays intersected = sum of active-list sizes in the reference's loop (Render.cpp:237-238) */
+    uint64_t shaded_hits;   /* hits that reached accumulateAndBounce */
+    uint64_t iterations;    /* wavefront passes */
+    uint64_t kernel_launches;
+    uint32_t max_depth;     /* deepest path, in bounces */
+    uint32_t reserved;
+    float gpu_ms;           /* device time of the render, CUDA events on the scene's stream */
+    float intersect_ms, shade_ms, raygen_ms, accumulate_ms; /* mean device ms per launch of each stage kernel over the
+                                                               sampled passes (CORNELIS_RENDER_STAGE_TIMING) */
+} cornelis_render_stats;
+
+typedef struct cornelis_cuda_scene cornelis_cuda_scene;
+
+/* Progress callback: called on the calling thread between wavefront batches; return non-zero to abort
+ * (RenderSession::ProgressCallback, Render.hpp:18-19). */
+typedef int (*cornelis_progress_fn)(void *user, uint64_t samples_done, uint64_t samples_total);
+
+/* ---- library ---------------------------------------------------------------------------------------------------- */
+
+int cornelis_cuda_abi_version(void);
+const char *cornelis_cuda_last_error(void);
+int cornelis_cuda_device_count(int *count);
+
+/* ---- scene: replaces SceneData construction (Scene.cpp:40-53) + upload ------------------------------------------ */
+
+/* `materials` is the complete list as SceneDescription::materials() returns it (index 0 = the default material). */
+int cornelis_cuda_scene_create(int device, const cornelis_camera_desc *camera,
+                               const cornelis_sphere_desc *spheres, size_t n_spheres,
+                               const cornelis_plane_desc *planes, size_t n_planes,
+                               const cornelis_material_desc *materials, size_t n_materials,
+                               cornelis_cuda_scene **out_scene);
+int cornelis_cuda_scene_destroy(cornelis_cuda_scene *scene);
+
+/* Run this scene's kernels and copies on the caller's stream (a cudaStream_t passed as void*; NULL restores the
+ * scene's own non-blocking stream).  Lets a host framework bracket the work with its own events. */
+int cornelis_cuda_scene_set_stream(cornelis_cuda_scene *scene, void *cuda_stream);
+
+/* ---- the hot path: replaces the tile loop + integrateTile (Render.cpp:220-255, 327-354) ------------------------- */
+
+/* Render the sample range into the device accumulators (sum of per-sample radiance per pixel). */
+int cornelis_cuda_render_accumulate(cornelis_cuda_scene *scene, const cornelis_render_params *params,
+                                    cornelis_progress_fn progress, void *progress_user, cornelis_render_stats *stats);
+
+/* Device pointer of the accumulation buffer: width*height float4 (sum r, g, b, sample count), for the cross-GPU sum
+ * (one all-reduce of n_floats floats).  Valid until the next render with a different frame size or scene destroy. */
+int cornelis_cuda_framebuffer_device(cornelis_cuda_scene *scene, void **device_ptr, size_t *n_floats);
+
+/* color = sum * (1.0f / samples) (Render.cpp:250) and download: host_rgb[3*W*H]; host_variance[3*W*H] optional
+ * (unbiased per-sample variance, only after a CORNELIS_RENDER_VARIANCE render). */
+int cornelis_cuda_resolve(cornelis_cuda_scene *scene, int32_t samples, float *host_rgb, float *host_variance);
+
+/* Same, followed by the display transform and 8-bit quantisation on the device (Color.cpp:64-80,
+ * FrameBuffer.hpp:91-95, i.e. what saveImage does before stbi_write_png, Render.cpp:257-265): host_rgb8[3*W*H]. */
+int cornelis_cuda_resolve_srgb8(cornelis_cuda_scene *scene, int32_t samples, uint8_t *host_rgb8);
+
+/* render_accumulate + resolve: scene in HBM, framebuffer back on the host — the end-to-end call. */
+int cornelis_cuda_render(cornelis_cuda_scene *scene, const cornelis_render_params *params, float *host_rgb,
+                         cornelis_render_stats *stats);
+
+/* ---- stage entry points (parity tests and the intersection microbench); host buffers, packed xyz --------------- */
+
+/* generateCameraRays arithmetic (Render.cpp:29-37, 85-100; Camera.cpp:11-13) for explicit jitter. */
+int cornelis_cuda_pixel_rays(cornelis_cuda_scene *scene, int32_t width, int32_t height, size_t n, const int32_t *pi,
+                             const int32_t *pj, const float *phi1, const float *phi2, float *org, float *dir);
+
+/* Closest hit over all spheres then all planes (Render.cpp:110-140, Geometry.cpp:34-178).  prim = sphere index, or
+ * n_spheres + plane index, or -1 (t = +inf).  P, N, mat may be NULL. */
+int cornelis_cuda_intersect(cornelis_cuda_scene *scene, size_t n, const float *org, const float *dir, float *t,
+                            int32_t *prim, float *P, float *N, int32_t *mat);
+
+/* Same kernel on device-resident float4 ray arrays (org.xyz|-, dir.xyz|-) writing float2 hits (t, prim as int bits);
+ * repeats the launch `repeats` times and returns the mean device milliseconds per launch. */
+int cornelis_cuda_intersect_device(cornelis_cuda_scene *scene, size_t n, const void *d_org4, const void *d_dir4,
+                                   void *d_hit2, int repeats, float *ms_per_launch);
+
+/* LayeredBRDF::generateDirection / operator() / pdf (Materials.hpp:255-293) on explicit inputs. */
+int cornelis_cuda_bsdf_sample(cornelis_cuda_scene *scene, size_t n, const int32_t *mat, const float *wo,
+                              const float *N, const float *x, float *wi, float *pdf, float *f);
+int cornelis_cuda_bsdf_eval(cornelis_cuda_scene *scene, size_t n, const int32_t *mat, const float *wi,
+                            const float *wo, const float *N, float *f, float *pdf);
+
+/* One accumulateAndBounce pass (Render.cpp:167-218) with explicit random numbers u[4*n] = (RR draw, x0, x1, x2).
+ * In/out org, dir, thr, rad (3*n); in P, N (3*n), mat (n); out alive (n). */
+int cornelis_cuda_shade(cornelis_cuda_scene *scene, size_t n, int32_t depth, const float *u, const float *P,
+                        const float *N, const int32_t *mat, float *org, float *dir, float *thr, float *rad,
+                        uint8_t *alive);
+
+/* The counter-based generator that replaces the per-tile xoshiro stream (PRNG.hpp:11-37): Philox4x32-10 keyed by
+ * `seed`, counter (pixel, sample, dimension block).  out[4*n] = the four U[0,1) floats of each counter, with the
+ * reference's 24-bit mapping (u >> 8) * 2^-24 (XoshiroCpp.hpp:651-655).  Block 0 feeds the camera jitter, block
+ * d+1 the bounce at depth d. */
+int cornelis_cuda_rng_uniforms(cornelis_cuda_scene *scene, uint64_t seed, size_t n, const uint32_t *pixel,
+                               const uint32_t *sample, const uint32_t *block, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CORNELIS_CUDA_H */

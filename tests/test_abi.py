@@ -1,0 +1,84 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/cornelis_cuda.h
+declares, and fails loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "cornelis_cuda.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cornelis_cuda_\w+)\s*\(", text)))
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary header must compile as C (no C++ types in the signatures)."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "cornelis_cuda.h"\nint main(void){return (int)sizeof(cornelis_render_params) == 0;}\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", str(ROOT / "include"), "-c", str(src),
+                    "-o", str(tmp_path / "abi.o")], check=True)
+
+
+def test_library_exports_every_declared_symbol():
+    from cornelis_b200 import binding
+    if not binding.LIB_PATH.exists():
+        from cornelis_b200 import build
+        build.build_cuda()
+    lib = binding.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    assert sorted(binding.EXPORTS) == declared
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.cornelis_cuda_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from cornelis_b200 import binding
+    assert C.sizeof(binding.CameraDesc) == 32 and C.sizeof(binding.MaterialDesc) == 44
+    assert C.sizeof(binding.SphereDesc) == 20 and C.sizeof(binding.PlaneDesc) == 40
+    assert C.sizeof(binding.RenderParams) == 48
+    assert C.sizeof(binding.RenderStats) == 72
+
+
+def test_no_device_fails_loudly():
+    """Without a GPU the product must refuse to compute — there is no CPU path to fall back to."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from cornelis_b200 import binding, scenes
+    with pytest.raises(binding.CornelisError) as e:
+        binding.device_count()
+    assert e.value.code == binding.ERR_NO_DEVICE
+    with pytest.raises(binding.CornelisError) as e:
+        binding.Scene(scenes.cornell_box())
+    assert e.value.code == binding.ERR_NO_DEVICE and "no CPU path" in str(e.value)
+
+
+def test_product_does_not_touch_the_oracle():
+    """Nothing under cornelis_b200/, include/ or the host sources may reference oracle/ or /root/reference."""
+    offenders = []
+    for base in (ROOT / "cornelis_b200", ROOT / "include"):
+        for path in base.rglob("*"):
+            if path.is_file() and path.suffix in {".py", ".cu", ".cuh", ".h", ".hpp", ".cpp"}:
+                text = path.read_text(errors="ignore")
+                if re.search(r"\boracle[/.]|ora_[a-z]+\(|libcornelis_(ref|oracle)|/root/reference", text):
+                    offenders.append(str(path.relative_to(ROOT)))
+    assert not offenders, offenders
+
+
+def test_scene_fixtures_are_well_formed():
+    from cornelis_b200 import scenes
+    c = scenes.cornell_box()
+    assert c["spheres"].shape == (4, 4) and c["planes"].shape == (5, 9) and c["materials"].shape == (5, 11)
+    m = scenes.microbench_scene(1024)
+    assert m["spheres"].shape == (1024, 4) and m["planes"].shape == (6, 9)
+    assert (m["sphere_mat"] == np.arange(1024) % 6).all() and (m["plane_mat"] == (1024 + np.arange(6)) % 6).all()
+    o, d = scenes.microbench_rays(1000)
+    assert np.allclose(np.linalg.norm(d, axis=1), 1, atol=1e-6) and np.abs(o).max() <= 1000

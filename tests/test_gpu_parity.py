@@ -1,0 +1,339 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the oracle on identical inputs.
+
+Bars (BASELINE.json north_star):
+  * intersection: hit primitive ids bit-exact, t within 2 ulp (we require bit-exact: 0 ulp)
+  * material sample / eval on fixed random inputs: 1e-5 relative
+  * converged images: per-pixel within 3 sigma of the Monte-Carlo estimator, RMSE stated
+"""
+import numpy as np
+import pytest
+
+from cornelis_b200 import scenes
+from conftest import bit_equal, ulp_distance
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5  # material parity tolerance (north_star)
+
+
+@pytest.fixture(scope="module")
+def binding():
+    from cornelis_b200 import binding as b
+    assert b.device_count() >= 1
+    return b
+
+
+@pytest.fixture(scope="module")
+def oracle(port_oracle, ref_oracle):
+    return ref_oracle if ref_oracle is not None else port_oracle
+
+
+def unit(rng, n):
+    v = rng.standard_normal((n, 3)).astype(np.float32)
+    return (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+
+
+def rel_err(a, b, floor=1e-3):
+    """|a-b| / max(|b|, floor) per vector (3-vectors are judged on their norm, scalars on their magnitude)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    if a.ndim == 2:
+        return np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), floor)
+    return np.abs(a - b) / np.maximum(np.abs(b), floor)
+
+
+# ------------------------------------------------------------------------------------------------- camera rays --
+
+def test_pixel_rays_bit_exact(binding, oracle, golden):
+    g = golden("pixel_rays_1080p.npz")
+    flat = scenes.cornell_box(aspect=0.5625)
+    sc = binding.Scene(flat)
+    o, d = sc.pixel_rays(int(g["W"]), int(g["H"]), g["pi"], g["pj"], g["phi1"], g["phi2"])
+    assert bit_equal(o, g["org"]) and bit_equal(d, g["dir"])
+    rng = np.random.default_rng(5)
+    for W, H, aspect in ((512, 512, 1.0), (3840, 2160, 0.5625), (50, 30, 0.6)):
+        flat = scenes.cornell_box(aspect=aspect)
+        n = 50000
+        pi, pj = rng.integers(0, W, n), rng.integers(0, H, n)
+        p1, p2 = rng.random(n, dtype=np.float32), rng.random(n, dtype=np.float32)
+        a = binding.Scene(flat).pixel_rays(W, H, pi, pj, p1, p2)
+        b = oracle.scene(flat).pixel_rays(W, H, pi, pj, p1, p2)
+        assert bit_equal(a[0], b[0]) and bit_equal(a[1], b[1])
+
+
+# ------------------------------------------------------------------------------------------------ intersection --
+
+@pytest.mark.parametrize("name,flat", [("intersect_microbench.npz", scenes.microbench_scene(1024)),
+                                       ("intersect_cornell.npz", scenes.cornell_box())])
+def test_intersect_golden(binding, golden, name, flat):
+    g = golden(name)
+    h = binding.Scene(flat).intersect(g["org"], g["dir"])
+    assert np.array_equal(h["prim"], g["prim"]), "hit primitive ids must be bit-exact"
+    assert ulp_distance(h["t"], g["t"]).max() == 0
+    assert bit_equal(h["P"], g["P"]) and bit_equal(h["N"], g["N"]) and np.array_equal(h["mat"], g["mat"])
+
+
+def test_intersect_against_oracle_large(binding, oracle):
+    """Config 3 at oracle-friendly size (2^20 rays x 1024 spheres + 6 planes) plus ragged / degenerate batches."""
+    flat = scenes.microbench_scene(1024)
+    sc, osc = binding.Scene(flat), oracle.scene(flat)
+    org, dirs = scenes.microbench_rays(1 << 20)
+    a, b = sc.intersect(org, dirs), osc.intersect(org, dirs)
+    assert np.array_equal(a["prim"], b["prim"])
+    assert ulp_distance(a["t"], b["t"]).max() == 0
+    assert bit_equal(a["P"], b["P"]) and bit_equal(a["N"], b["N"]) and np.array_equal(a["mat"], b["mat"])
+    assert (a["prim"] >= 0).all()  # closed box: every ray hits something
+    # ragged sizes, non-unit and zero directions
+    rng = np.random.default_rng(11)
+    for n in (1, 31, 257, 1000):
+        o = (rng.random((n, 3), dtype=np.float32) * 1800 - 900).astype(np.float32)
+        d = (unit(rng, n) * rng.random((n, 1), dtype=np.float32) * 4).astype(np.float32)
+        d[::7] = 0
+        d[1::7] *= np.float32(1e-5)
+        a, b = sc.intersect(o, d), osc.intersect(o, d)
+        assert np.array_equal(a["prim"], b["prim"]) and bit_equal(a["t"], b["t"])
+        assert (a["prim"][::7] == -1).all() and np.isinf(a["t"][::7]).all()
+    empty = sc.intersect(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+    assert len(empty["t"]) == 0
+
+
+def test_intersect_full_size_properties(binding, oracle):
+    """Config 3 at BASELINE size: 2^24 rays.  The oracle checks a strided 2^19 subset bit for bit; the whole batch
+    is checked through size-independent properties (determinism, hits lie on their primitive)."""
+    flat = scenes.microbench_scene(1024)
+    sc = binding.Scene(flat)
+    n = 1 << 24
+    org, dirs = scenes.microbench_rays(n)
+    a = sc.intersect(org, dirs, surface=False)
+    again = sc.intersect(org, dirs, surface=False)
+    assert np.array_equal(a["prim"], again["prim"]) and bit_equal(a["t"], again["t"])  # idempotent / deterministic
+    sel = slice(0, n, 32)
+    b = oracle.scene(flat).intersect(org[sel], dirs[sel])
+    assert np.array_equal(a["prim"][sel], b["prim"]) and ulp_distance(a["t"][sel], b["t"]).max() == 0
+    # every sphere hit lies on its sphere (|P - c| = r within fp32 slack), every plane hit on its plane
+    t, prim = a["t"].astype(np.float64), a["prim"]
+    P = org.astype(np.float64) + dirs.astype(np.float64) * t[:, None]
+    sph = prim < 1024
+    c = flat["spheres"][prim[sph]].astype(np.float64)
+    r = np.linalg.norm(P[sph] - c[:, :3], axis=1)
+    err = np.abs(r - c[:, 3])  # grazing hits amplify the fp32 rounding of the discriminant (reference algorithm)
+    assert np.quantile(err, 0.999) < 0.02 and err.max() < 1.0
+    pl = flat["planes"][prim[~sph] - 1024].astype(np.float64)
+    dist = ((P[~sph] - pl[:, 3:6]) * pl[:, 0:3]).sum(1)
+    assert np.abs(dist).max() < 0.05
+    assert (t >= 0).all() and np.isfinite(t).all()
+    assert 0.2 < sph.mean() < 0.35
+
+
+# ---------------------------------------------------------------------------------------------------- materials --
+
+def _bsdf_inputs(rng, n, n_mat):
+    N = unit(rng, n)
+    N[: n // 16] = np.float32([0, 1, 0])
+    N[n // 16: n // 8] = np.float32([0, 0, -1])
+    wo = unit(rng, n)
+    flip = (wo * N).sum(1) < 0
+    wo[flip] = -wo[flip]
+    x = rng.random((n, 3), dtype=np.float32)
+    mat = rng.integers(0, n_mat, n).astype(np.int32)
+    return mat, wo, N, x
+
+
+def test_bsdf_sample_and_eval(binding, oracle, golden):
+    flat = scenes.cornell_box()
+    sc, osc = binding.Scene(flat), oracle.scene(flat)
+    g = golden("bsdf_cornell.npz")
+    s = sc.bsdf_sample(g["mat"], g["wo"], g["N"], g["x"])
+    assert rel_err(s["wi"], g["wi"], 1.0).max() <= REL
+    assert rel_err(s["pdf"], g["pdf"]).max() <= REL and rel_err(s["f"], g["f"]).max() <= REL
+    e = sc.bsdf_eval(g["mat"], g["eval_wi"], g["wo"], g["N"])
+    assert rel_err(e["f"], g["eval_f"]).max() <= REL and rel_err(e["pdf"], g["eval_pdf"]).max() <= REL
+
+    rng = np.random.default_rng(23)
+    for flat in (scenes.cornell_box(), scenes.many_spheres(16, 64)):
+        sc, osc = binding.Scene(flat), oracle.scene(flat)
+        n = 1 << 18
+        mat, wo, N, x = _bsdf_inputs(rng, n, len(flat["materials"]) + 1)
+        a, b = sc.bsdf_sample(mat, wo, N, x), osc.bsdf_sample(mat, wo, N, x)
+        # lobe choice / early-outs are decided by identical comparisons on identical inputs
+        assert np.array_equal((a["wi"] == 0).all(1), (b["wi"] == 0).all(1))
+        err = np.maximum.reduce([rel_err(a["wi"], b["wi"], 1.0), rel_err(a["pdf"], b["pdf"]), rel_err(a["f"], b["f"])])
+        assert err.max() <= REL, (err.max(), int(err.argmax()))
+        wi = unit(rng, n)
+        a, b = sc.bsdf_eval(mat, wi, wo, N), osc.bsdf_eval(mat, wi, wo, N)
+        err = np.maximum(rel_err(a["f"], b["f"]), rel_err(a["pdf"], b["pdf"]))
+        assert err.max() <= REL, (err.max(), int(err.argmax()))
+        assert not np.isnan(a["f"]).any()
+
+
+def test_shade_step(binding, oracle, golden):
+    """One accumulateAndBounce pass: RR decision identical, new ray / throughput / radiance within 1e-5."""
+    flat = scenes.cornell_box()
+    sc, osc = binding.Scene(flat), oracle.scene(flat)
+    g = golden("shade_cornell.npz")
+    order = g["order"]
+    for depth in (0, 5):
+        u = g[f"d{depth}_u"]
+        ux = np.stack([u[:, 0], u[:, 1 + order[0]], u[:, 1 + order[1]], u[:, 1 + order[2]]], axis=1)
+        r = sc.shade(depth, ux, g["P"], g["N"], g["mat"], g["org"], g["dir"], g["thr"], g["rad"])
+        alive = g[f"d{depth}_alive"]
+        assert np.array_equal(r["alive"], alive)
+        assert rel_err(r["rad"], g[f"d{depth}_rad"]).max() <= REL
+        for k in ("org", "dir", "thr"):
+            assert rel_err(r[k][alive], g[f"d{depth}_{k}"][alive], 1e-3).max() <= REL, (depth, k)
+    rng = np.random.default_rng(31)
+    n = 1 << 17
+    mat, wo, N, _ = _bsdf_inputs(rng, n, 6)
+    P = (rng.standard_normal((n, 3)) * 200).astype(np.float32)
+    thr = (rng.random((n, 3), dtype=np.float32) * 1.5).astype(np.float32)
+    rad = rng.random((n, 3), dtype=np.float32)
+    order = oracle.sample_draw_order()
+    for depth in (0, 2, 3, 7):
+        b = osc.shade(depth, 777, P, N, mat, P, -wo, thr, rad)
+        u = b["u"]
+        ux = np.stack([u[:, 0], u[:, 1 + order[0]], u[:, 1 + order[1]], u[:, 1 + order[2]]], axis=1)
+        a = sc.shade(depth, ux, P, N, mat, P, -wo, thr, rad)
+        assert np.array_equal(a["alive"], b["alive"])
+        live = b["alive"]
+        assert rel_err(a["rad"], b["rad"]).max() <= REL
+        assert rel_err(a["dir"][live], b["dir"][live], 1.0).max() <= REL
+        assert rel_err(a["org"][live], b["org"][live], 1.0).max() <= REL
+        assert rel_err(a["thr"][live], b["thr"][live]).max() <= REL
+
+
+# ---------------------------------------------------------------------------------------------------------- rng --
+
+def _philox_numpy(c0, c1, c2, k0, k1):
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85)
+    mask, sh = np.uint64(0xFFFFFFFF), np.uint64(32)
+    c = [c0.astype(np.uint64), c1.astype(np.uint64), c2.astype(np.uint64), np.zeros_like(c0, np.uint64)]
+    k0, k1 = np.uint64(k0), np.uint64(k1)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [(p1 >> sh) ^ c[1] ^ k0, p1 & mask, (p0 >> sh) ^ c[3] ^ k1, p0 & mask]
+        k0, k1 = (k0 + W0) & mask, (k1 + W1) & mask
+    return np.stack(c, axis=1).astype(np.uint32)
+
+
+def test_counter_rng(binding):
+    sc = binding.Scene(scenes.cornell_box())
+    rng = np.random.default_rng(3)
+    n = 1 << 16
+    pixel = rng.integers(0, 1 << 23, n).astype(np.uint32)
+    sample = rng.integers(0, 1 << 14, n).astype(np.uint32)
+    block = rng.integers(0, 16, n).astype(np.uint32)
+    seed = 19791102 | (7 << 32)
+    u = sc.rng_uniforms(seed, pixel, sample, block)
+    bits = _philox_numpy(pixel, sample, block, seed & 0xFFFFFFFF, seed >> 32)
+    expect = (bits >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)  # XoshiroCpp.hpp:651-655 mapping
+    assert bit_equal(u, expect)
+    assert (u >= 0).all() and (u < 1).all()
+    assert abs(u.mean() - 0.5) < 0.005 and abs(u.var() - 1 / 12) < 0.002
+    # Random123 known-answer vector for philox4x32-10: counter 0, key 0
+    z = np.zeros(1, np.uint32)
+    assert [hex(v) for v in _philox_numpy(z, z, z, 0, 0)[0]] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+
+
+# ------------------------------------------------------------------------------------------------------- images --
+
+def _three_sigma(mu_g, var_g, n_g, mu_r, var_r, n_r):
+    sigma = np.sqrt(var_r.astype(np.float64) / n_r + var_g.astype(np.float64) / n_g)
+    diff = np.abs(mu_g.astype(np.float64) - mu_r.astype(np.float64))
+    ok = diff <= 3.0 * sigma + 1e-4 * (1.0 + np.abs(mu_r))
+    return ok, diff, sigma
+
+
+def test_converged_image_within_three_sigma(binding, golden):
+    """Cornell box 128x128: GPU 4096 spp against the reference's own 4096 spp render (mean + per-sample variance from
+    the compiled reference, tests/golden/make_golden.py)."""
+    g = golden("render_cornell_128x128_4096spp.npz")
+    sc = binding.Scene(scenes.cornell_box())
+    spp = 4096
+    st = sc.render_accumulate(128, 128, spp, variance=True)
+    mean, var = sc.resolve(spp, variance=True)
+    ok, diff, sigma = _three_sigma(mean, var, spp, g["mean"], g["variance"], int(g["spp"]))
+    # The reference's Oren-Nayar term turns NaN when |w.z| rounds above 1 (about once per 1e8 samples, see
+    # include/cornelis_cuda.h CORNELIS_RENDER_DROP_NONFINITE); such pixels count as failures of the 3-sigma test.
+    bad = ~np.isfinite(mean).all(axis=2)
+    assert bad.sum() <= 3, bad.sum()
+    frac = ok.mean()
+    good = ~bad
+    rmse = float(np.sqrt(np.mean(diff[good] ** 2)))
+    rel_rmse = rmse / float(np.sqrt(np.mean(g["mean"].astype(np.float64) ** 2)))
+    energy = float(mean[good].mean() / g["mean"][good].mean())
+    print(f"3-sigma fraction {frac:.5f}  RMSE {rmse:.5f}  relRMSE {rel_rmse:.5f}  energy ratio {energy:.5f} "
+          f"non-finite pixels {int(bad.sum())}")
+    assert frac >= 0.99, frac                # 0.9973 for a normal estimator; the heavy tail costs a little
+    assert abs(energy - 1.0) < 0.01
+    assert rel_rmse < 0.05
+    z = (mean.astype(np.float64) - g["mean"]) / np.maximum(sigma, 1e-9)
+    zz = z[(sigma > 1e-6) & np.isfinite(z)]
+    assert abs(zz.mean()) < 0.05 and 0.8 < zz.std() < 1.2  # unbiased, correctly scaled
+    rays_per_sample = st["rays"] / st["pixel_samples"]
+    ref_rays_per_sample = float(g["rays"]) / (128 * 128 * int(g["spp"]))
+    assert abs(rays_per_sample - ref_rays_per_sample) < 0.01, (rays_per_sample, ref_rays_per_sample)
+    assert st["pixel_samples"] == 128 * 128 * spp and 8 <= st["max_depth"] <= 40
+
+
+def test_render_against_oracle_other_scene(binding, oracle):
+    """A second scene (mixed materials, many-sphere style) at a frame that is not a multiple of anything."""
+    flat = scenes.many_spheres(60, 12, aspect=0.6)
+    W, H, spp_ref, spp = 50, 30, 1024, 2048
+    ref = oracle.scene(flat).render(W, H, spp_ref, tile=(10, 10), variance=True, stats=True)
+    sc = binding.Scene(flat)
+    st = sc.render_accumulate(W, H, spp, variance=True)
+    mean, var = sc.resolve(spp, variance=True)
+    ok, diff, sigma = _three_sigma(mean, var, spp, ref["mean"], ref["variance"], spp_ref)
+    assert ok.mean() >= 0.985, ok.mean()
+    sc.render_accumulate(W, H, 256, drop_nonfinite=True)
+    assert np.isfinite(sc.resolve(256)).all()
+    assert abs(st["rays"] / st["pixel_samples"] - ref["stats"]["rays"] / ref["stats"]["pixel_samples"]) < 0.03
+
+
+def test_sample_sharding_and_determinism(binding):
+    """Sample ranges add up: [0,32) + [32,64) accumulated == [0,64) (same sample set; fp32 sums differ only by
+    atomic ordering), and the image does not depend on the pool size."""
+    sc = binding.Scene(scenes.cornell_box())
+    W = H = 96
+    sc.render_accumulate(W, H, 64)
+    whole = sc.resolve(64).copy()
+    sc.render_accumulate(W, H, 64, first_sample=0, sample_count=32)
+    sc.render_accumulate(W, H, 64, first_sample=32, sample_count=32, keep=True)
+    parts = sc.resolve(64)
+    assert np.allclose(whole, parts, rtol=1e-5, atol=1e-6)
+    sc.render_accumulate(W, H, 64, pool_paths=4096)
+    small_pool = sc.resolve(64)
+    assert np.allclose(whole, small_pool, rtol=1e-5, atol=1e-6)
+    other_seed, _ = sc.render(W, H, 64, seed=12345)
+    assert not np.allclose(whole, other_seed, rtol=1e-3, atol=1e-4)
+
+
+def test_render_end_to_end_and_display_transform(binding, oracle):
+    sc = binding.Scene(scenes.cornell_box())
+    img, st = sc.render(64, 48, 16)
+    assert img.shape == (48, 64, 3) and np.isfinite(img).all() and img.max() > 1.0 and st["kernel_launches"] > 0
+    again = sc.resolve(16)
+    assert bit_equal(img, again)
+    srgb = sc.resolve_srgb8(16)
+    expect = oracle.to_srgb8(img.reshape(-1, 3)).reshape(48, 64, 3)
+    assert np.abs(srgb.astype(int) - expect.astype(int)).max() <= 1 and (srgb == expect).mean() > 0.999
+    # top row is j = 0: the light (bright) is in the upper half, the floor in the lower
+    assert img[:24].mean() > 0
+
+
+def test_depth_cap_and_argument_errors(binding):
+    sc = binding.Scene(scenes.cornell_box())
+    st = sc.render_accumulate(64, 64, 8, max_depth=2)
+    assert st["max_depth"] <= 2
+    st = sc.render_accumulate(64, 64, 8)
+    assert st["max_depth"] > 2
+    for bad in (dict(width=0, height=16, samples=4), dict(width=16, height=16, samples=0),
+                dict(width=16, height=-1, samples=4)):
+        with pytest.raises(binding.CornelisError) as e:
+            sc.render_accumulate(bad["width"], bad["height"], bad["samples"])
+        assert e.value.code == binding.ERR_INVALID_ARGUMENT
+    with pytest.raises(binding.CornelisError):
+        sc.bsdf_eval([99], [[0, 0, 1]], [[0, 0, 1]], [[0, 0, 1]])
+    calls = []
+    with pytest.raises(binding.CornelisError) as e:
+        sc.render_accumulate(256, 256, 64, pool_paths=65536, progress=lambda done, total: calls.append(done) or 1)
+    assert e.value.code == binding.ERR_ABORTED and len(calls) == 1
