@@ -17,7 +17,8 @@ LIB_PATH = Path(__file__).resolve().parent / "lib" / "libcornelis_cuda.so"
 EXPORTS = [
     "cornelis_cuda_abi_version", "cornelis_cuda_last_error", "cornelis_cuda_device_count",
     "cornelis_cuda_scene_create", "cornelis_cuda_scene_destroy", "cornelis_cuda_scene_set_stream", "cornelis_cuda_render_accumulate",
-    "cornelis_cuda_framebuffer_device", "cornelis_cuda_resolve", "cornelis_cuda_resolve_srgb8",
+    "cornelis_cuda_framebuffer_device", "cornelis_cuda_resolve", "cornelis_cuda_resolve_device",
+    "cornelis_cuda_resolve_srgb8",
     "cornelis_cuda_render", "cornelis_cuda_pixel_rays", "cornelis_cuda_intersect",
     "cornelis_cuda_intersect_device", "cornelis_cuda_bsdf_sample", "cornelis_cuda_bsdf_eval",
     "cornelis_cuda_shade", "cornelis_cuda_rng_uniforms",
@@ -94,6 +95,7 @@ def lib():
         L.cornelis_cuda_framebuffer_device.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
         L.cornelis_cuda_resolve.argtypes = [vp, i32, vp, vp]
         L.cornelis_cuda_resolve_srgb8.argtypes = [vp, i32, vp]
+        L.cornelis_cuda_resolve_device.argtypes = [vp, i32, C.POINTER(vp)]
         L.cornelis_cuda_render.argtypes = [vp, C.POINTER(RenderParams), vp, C.POINTER(RenderStats)]
         L.cornelis_cuda_pixel_rays.argtypes = [vp, i32, i32, sz, f, f, f, f, f, f]
         L.cornelis_cuda_intersect.argtypes = [vp, sz, f, f, f, f, f, f, f]
@@ -223,6 +225,12 @@ class Scene:
         var = np.empty((H, W, 3), np.float32) if variance else None
         _check(lib().cornelis_cuda_resolve(self.handle, samples, _ptr(rgb), _ptr(var)))
         return (rgb, var) if variance else rgb
+
+    def resolve_device(self, samples):
+        """Resolve on the device only; returns the device pointer of the packed RGB image."""
+        ptr = C.c_void_p()
+        _check(lib().cornelis_cuda_resolve_device(self.handle, samples, C.byref(ptr)))
+        return ptr.value
 
     def resolve_srgb8(self, samples):
         W, H = self.frame

@@ -500,6 +500,23 @@ int cornelis_cuda_resolve(cornelis_cuda_scene *s, int32_t samples, float *hostRg
     return CORNELIS_OK;
 }
 
+int cornelis_cuda_resolve_device(cornelis_cuda_scene *s, int32_t samples, void **deviceRgb) {
+    if (int rc = checkScene(s))
+        return rc;
+    if (samples <= 0 || !deviceRgb)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "samples must be > 0 and device_rgb non-null");
+    if (!s->accum.ptr || !s->width)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "nothing has been rendered yet");
+    size_t const npix = static_cast<size_t>(s->width) * s->height;
+    CB_CUDA(s->outRgb.reserve(3 * npix));
+    launchResolve(s->stream, s->shape, static_cast<uint32_t>(npix), static_cast<uint32_t>(samples), s->accum.ptr, nullptr,
+                  s->outRgb.ptr, nullptr);
+    CB_CUDA(cudaStreamSynchronize(s->stream));
+    CB_CUDA(cudaGetLastError());
+    *deviceRgb = s->outRgb.ptr;
+    return CORNELIS_OK;
+}
+
 int cornelis_cuda_resolve_srgb8(cornelis_cuda_scene *s, int32_t samples, uint8_t *hostRgb8) {
     if (int rc = checkScene(s))
         return rc;

@@ -149,7 +149,10 @@ int cornelis_cuda_framebuffer_device(cornelis_cuda_scene *scene, void **device_p
  * (unbiased per-sample variance, only after a CORNELIS_RENDER_VARIANCE render). */
 int cornelis_cuda_resolve(cornelis_cuda_scene *scene, int32_t samples, float *host_rgb, float *host_variance);
 
-/* Same, followed by the display transform and 8-bit quantisation on the device (Color.cpp:64-80,
+/* The resolve alone: packed RGB (3*W*H floats) left in device memory owned by the scene; no host copy. */
+int cornelis_cuda_resolve_device(cornelis_cuda_scene *scene, int32_t samples, void **device_rgb);
+
+/* Same as cornelis_cuda_resolve, followed by the display transform and 8-bit quantisation on the device (Color.cpp:64-80,
  * FrameBuffer.hpp:91-95, i.e. what saveImage does before stbi_write_png, Render.cpp:257-265): host_rgb8[3*W*H]. */
 int cornelis_cuda_resolve_srgb8(cornelis_cuda_scene *scene, int32_t samples, uint8_t *host_rgb8);
 
