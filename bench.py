@@ -249,6 +249,7 @@ def ours(args, flat):
     import torch.distributed as dist
 
     from cornelis_b200 import binding
+    from cornelis_b200.sharding import sample_range, sum_framebuffers
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -263,11 +264,7 @@ def ours(args, flat):
 
     W, H = args.width, args.height
     npix = W * H
-    if args.scaling == "weak":
-        total_spp, count, first = args.spp * world, args.spp, rank * args.spp
-    else:
-        count = args.spp // world
-        total_spp, first = count * world, rank * count
+    first, count, total_spp = sample_range(rank, world, args.spp, args.scaling)
     stream = torch.cuda.Stream()
     scene = binding.Scene(flat, device=local_rank)
     scene.set_stream(stream.cuda_stream)
@@ -279,7 +276,7 @@ def ours(args, flat):
         if world > 1:
             ptr, n = sc.framebuffer_device()
             fb = torch.as_tensor(DeviceArray(ptr, n), device=f"cuda:{local_rank}")
-            dist.all_reduce(fb, op=dist.ReduceOp.SUM)
+            sum_framebuffers(fb)
             launches[0] += 1
 
     def step_device(collect=None):
@@ -341,7 +338,7 @@ def ours(args, flat):
     e2e_dev_s, e2e_wall_s = timed(step_e2e, args.steps)
 
     # whole-job totals: every rank renders the same amount
-    samples_per_step = float(npix) * count * world
+    samples_per_step = float(npix) * total_spp
     rays_per_step = statistics.mean(s["rays"] for s in collected) * world
     if world > 1:
         dist.barrier()

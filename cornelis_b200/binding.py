@@ -17,7 +17,7 @@ LIB_PATH = Path(__file__).resolve().parent / "lib" / "libcornelis_cuda.so"
 EXPORTS = [
     "cornelis_cuda_abi_version", "cornelis_cuda_last_error", "cornelis_cuda_device_count",
     "cornelis_cuda_scene_create", "cornelis_cuda_scene_destroy", "cornelis_cuda_scene_set_stream", "cornelis_cuda_render_accumulate",
-    "cornelis_cuda_framebuffer_device", "cornelis_cuda_resolve", "cornelis_cuda_resolve_device",
+    "cornelis_cuda_framebuffer_device", "cornelis_cuda_reduce_framebuffers", "cornelis_cuda_resolve", "cornelis_cuda_resolve_device",
     "cornelis_cuda_resolve_srgb8",
     "cornelis_cuda_render", "cornelis_cuda_pixel_rays", "cornelis_cuda_intersect",
     "cornelis_cuda_intersect_device", "cornelis_cuda_bsdf_sample", "cornelis_cuda_bsdf_eval",
@@ -94,6 +94,7 @@ def lib():
         L.cornelis_cuda_render_accumulate.argtypes = [vp, C.POINTER(RenderParams), vp, vp, C.POINTER(RenderStats)]
         L.cornelis_cuda_framebuffer_device.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
         L.cornelis_cuda_resolve.argtypes = [vp, i32, vp, vp]
+        L.cornelis_cuda_reduce_framebuffers.argtypes = [C.POINTER(vp), C.c_int]
         L.cornelis_cuda_resolve_srgb8.argtypes = [vp, i32, vp]
         L.cornelis_cuda_resolve_device.argtypes = [vp, i32, C.POINTER(vp)]
         L.cornelis_cuda_render.argtypes = [vp, C.POINTER(RenderParams), vp, C.POINTER(RenderStats)]
@@ -117,6 +118,12 @@ def device_count() -> int:
     n = C.c_int(0)
     _check(lib().cornelis_cuda_device_count(C.byref(n)))
     return n.value
+
+
+def reduce_framebuffers(scene_list):
+    """Sum the accumulators of several scenes (one per GPU, single process) into the first."""
+    arr = (C.c_void_p * len(scene_list))(*[s.handle for s in scene_list])
+    _check(lib().cornelis_cuda_reduce_framebuffers(arr, len(scene_list)))
 
 
 def _ptr(a):

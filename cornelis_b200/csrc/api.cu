@@ -477,6 +477,57 @@ int cornelis_cuda_framebuffer_device(cornelis_cuda_scene *s, void **devicePtr, s
     return CORNELIS_OK;
 }
 
+int cornelis_cuda_reduce_framebuffers(cornelis_cuda_scene *const *scenes, int n) {
+    if (!scenes || n <= 0 || !scenes[0])
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "no scenes to reduce");
+    cornelis_cuda_scene *root = scenes[0];
+    size_t const npix = static_cast<size_t>(root->width) * root->height;
+    if (!root->accum.ptr || !npix)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "nothing has been rendered yet");
+    for (int k = 1; k < n; k++) {
+        cornelis_cuda_scene *peer = scenes[k];
+        if (!peer || peer->width != root->width || peer->height != root->height || !peer->accum.ptr ||
+            peer->haveVariance != root->haveVariance)
+            return fail(CORNELIS_ERR_INVALID_ARGUMENT, "scenes must hold renders of the same frame");
+        CB_CUDA(cudaSetDevice(peer->device));
+        CB_CUDA(cudaStreamSynchronize(peer->stream));
+    }
+    CB_CUDA(cudaSetDevice(root->device));
+    DeviceBuffer<float4> staging;
+    for (int k = 1; k < n; k++) {
+        cornelis_cuda_scene *peer = scenes[k];
+        int direct = peer->device == root->device;
+        if (!direct) {
+            CB_CUDA(cudaDeviceCanAccessPeer(&direct, root->device, peer->device));
+            if (direct) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled)
+                    cudaGetLastError();
+                else if (e != cudaSuccess)
+                    direct = 0;
+            }
+        }
+        const float4 *images[2] = {peer->accum.ptr, root->haveVariance ? peer->accum2.ptr : nullptr};
+        float4 *targets[2] = {root->accum.ptr, root->haveVariance ? root->accum2.ptr : nullptr};
+        for (int which = 0; which < 2; which++) {
+            if (!images[which])
+                continue;
+            const float4 *src = images[which];
+            if (!direct) {
+                CB_CUDA(staging.reserve(npix));
+                CB_CUDA(cudaMemcpyPeerAsync(staging.ptr, root->device, src, peer->device, npix * sizeof(float4),
+                                            root->stream));
+                src = staging.ptr;
+            }
+            launchAddImages(root->stream, root->shape, npix, targets[which], src);
+        }
+    }
+    CB_CUDA(cudaStreamSynchronize(root->stream));
+    CB_CUDA(cudaGetLastError());
+    staging.release();
+    return CORNELIS_OK;
+}
+
 int cornelis_cuda_resolve(cornelis_cuda_scene *s, int32_t samples, float *hostRgb, float *hostVariance) {
     if (int rc = checkScene(s))
         return rc;

@@ -226,6 +226,19 @@ __global__ void __launch_bounds__(kBlockThreads) k_resolve_srgb8(uint32_t npixel
     }
 }
 
+// dst += src over float4 images; src may live on a peer GPU (NVLink peer access): the loads go over the link, the
+// adds and stores are local.
+__global__ void __launch_bounds__(kBlockThreads) k_add_images(size_t n4, float4 *__restrict__ dst,
+                                                              const float4 *__restrict__ src) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        float4 a = dst[i];
+        float4 const b = src[i];
+        a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+        dst[i] = a;
+    }
+}
+
 // ------------------------------------------------------------------------------- stage kernels on plain arrays --
 
 __global__ void __launch_bounds__(kBlockThreads) k_pixel_rays(DevCamera cam, uint32_t n, float dx, float dy,
@@ -401,6 +414,10 @@ void launchResolveSrgb8(cudaStream_t s, const LaunchShape &shape, uint32_t npixe
                         const float4 *accum, uint8_t *rgb8) {
     float const inv = 1.0f / static_cast<float>(static_cast<int32_t>(samples));
     k_resolve_srgb8<<<gridFor(npixels, shape.numSMs, 8), kBlockThreads, 0, s>>>(npixels, inv, accum, rgb8);
+}
+
+void launchAddImages(cudaStream_t s, const LaunchShape &shape, size_t n4, float4 *dst, const float4 *src) {
+    k_add_images<<<gridFor(n4, shape.numSMs, 8), kBlockThreads, 0, s>>>(n4, dst, src);
 }
 
 void launchPixelRays(cudaStream_t s, const LaunchShape &shape, const DevCamera &cam, uint32_t n, float dx, float dy,

@@ -33,6 +33,8 @@ void launchResolve(cudaStream_t s, const LaunchShape &shape, uint32_t npixels, u
 void launchResolveSrgb8(cudaStream_t s, const LaunchShape &shape, uint32_t npixels, uint32_t samples,
                         const float4 *accum, uint8_t *rgb8);
 
+void launchAddImages(cudaStream_t s, const LaunchShape &shape, size_t n4, float4 *dst, const float4 *src);
+
 void launchPixelRays(cudaStream_t s, const LaunchShape &shape, const DevCamera &cam, uint32_t n, float dx, float dy,
                      const int32_t *pi, const int32_t *pj, const float *phi1, const float *phi2, float *org,
                      float *dir);

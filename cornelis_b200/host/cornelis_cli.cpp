@@ -1,0 +1,141 @@
+// The cornelis command line (reference src/cornelis.cpp): with no arguments it renders the Cornell box at 512x512,
+// 4096 spp, and writes cornelisrender2.png, as the reference binary does.  The reference ignores argv; the flags
+// below expose what it hard-codes.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include <cornelis/Render.hpp>
+#include <cornelis/SceneDescription.hpp>
+
+using namespace cornelis;
+
+// The benchmark fixture: five finite planes, four spheres, five materials (values of reference src/cornelis.cpp:6-74).
+static SceneDescription cornellBox(float aspect) {
+    float const side = 555.0f;
+    float const half = 550.0f / 2.0f;
+    SceneDescription scene;
+    PerspectiveCameraDescription cam;
+    cam.origin = V3(0, half, -1100);
+    cam.lookAt = V3(0, half, 0);
+    cam.aspect = aspect;
+    cam.horizontalFov = 0.7f;
+    scene.setCamera(cam);
+
+    auto matte = [](float r, float g, float b) {
+        MaterialDescription m;
+        m.albedo = RGB(r, g, b);
+        return m;
+    };
+    auto const red = scene.addMaterial(matte(.65f, .05f, .05f));
+    auto const white = scene.addMaterial(matte(.73f, .73f, .73f));
+    auto const green = scene.addMaterial(matte(.12f, .45f, .15f));
+    MaterialDescription goldDescr;
+    goldDescr.albedo = RGB::black();
+    goldDescr.roughness = 0.01f;
+    goldDescr.reflectionTint = RGB(0.916f, 0.61f, 0.0f);
+    goldDescr.ior = 0.470f;
+    auto const gold = scene.addMaterial(goldDescr);
+    MaterialDescription lightDescr;
+    lightDescr.albedo = RGB::black();
+    lightDescr.emissive = RGB(15, 15, 15);
+    auto const light = scene.addMaterial(lightDescr);
+
+    auto wall = [&](V3 normal, V3 point, std::size_t material) {
+        PlaneDescription p;
+        p.normal = normal;
+        p.point = point;
+        p.extents = V3(side, side, 0);
+        p.material = material;
+        scene.addPlane(p);
+    };
+    wall(V3(1, 0, 0), V3(-half, half, 0), green);   // left
+    wall(V3(-1, 0, 0), V3(half, half, 0), red);     // right
+    wall(V3(0, -1, 0), V3(0, side, 0), white);      // roof
+    wall(V3(0, 1, 0), V3(0, 0, 0), white);          // floor
+    wall(V3(0, 0, -1), V3(0, half, half), white);   // back
+
+    auto ball = [&](V3 center, float radius, std::size_t material) {
+        SphereDescription s;
+        s.center = center;
+        s.radius = radius;
+        s.material = material;
+        scene.addSphere(s);
+    };
+    ball(V3(0, side - 60.0f, 0), 60.0f, light);
+    ball(V3(0, 50.0f, 0), 50.0f, red);
+    ball(V3(-160, 100.0f, 0), 100.0f, white);
+    ball(V3(160, 125.0f, 200), 125.0f, gold);
+    return scene;
+}
+
+static void usage() {
+    std::puts("usage: cornelis [--width W] [--height H] [--spp N] [--aspect A] [--seed S] [--max-depth D]\n"
+              "                [--devices G] [--pool P] [--output file.png] [--no-save] [--drop-nonfinite] [--quiet]\n"
+              "defaults reproduce the reference CLI: 512x512, 4096 spp, cornelisrender2.png");
+}
+
+int main(int argc, char *argv[]) {
+    RenderOptions options;
+    options.samplesAA = 4096;
+    float aspect = -1.0f;
+    bool quiet = false;
+    for (int i = 1; i < argc; i++) {
+        std::string const a = argv[i];
+        auto next = [&]() -> char const * {
+            if (i + 1 >= argc) {
+                usage();
+                std::exit(2);
+            }
+            return argv[++i];
+        };
+        if (a == "--width") options.width = std::atoi(next());
+        else if (a == "--height") options.height = std::atoi(next());
+        else if (a == "--spp") options.samplesAA = std::atoi(next());
+        else if (a == "--aspect") aspect = static_cast<float>(std::atof(next()));
+        else if (a == "--seed") options.seed = std::strtoull(next(), nullptr, 10);
+        else if (a == "--max-depth") options.maxDepth = std::atoi(next());
+        else if (a == "--devices") options.devices = std::atoi(next());
+        else if (a == "--pool") options.poolPaths = std::atoi(next());
+        else if (a == "--output") options.outputPath = next();
+        else if (a == "--no-save") options.saveImage = false;
+        else if (a == "--drop-nonfinite") options.dropNonFinite = true;
+        else if (a == "--quiet") quiet = true;
+        else {
+            usage();
+            return a == "--help" || a == "-h" ? 0 : 2;
+        }
+    }
+    if (aspect <= 0.0f) // square pixels: the camera's aspect scales the vertical film vector
+        aspect = options.width > 0 ? static_cast<float>(options.height) / static_cast<float>(options.width) : 1.0f;
+    try {
+        RenderSession session(cornellBox(aspect), options);
+        auto const t0 = std::chrono::steady_clock::now();
+        int lastDecile = -1;
+        session.render([&](RenderProgress const &p, RenderStatus const &status) {
+            if (!quiet && p.samplesTotal) {
+                int const decile = static_cast<int>(10 * p.samplesDone / p.samplesTotal);
+                if (decile != lastDecile && status == RenderStatus::Running) {
+                    lastDecile = decile;
+                    std::fprintf(stderr, "%d%% done..\n", decile * 10);
+                }
+            }
+            return RenderCommand::Continue;
+        });
+        double const wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        auto const &st = session.statistics();
+        if (!quiet)
+            std::printf("%dx%d, %d spp, %d device(s): %.3f s wall, %.3f s on the GPU, %.1f Msamples/s, %.1f Mrays/s, "
+                        "%.3f rays/sample, deepest path %u%s%s\n",
+                        options.width, options.height, options.samplesAA, options.devices, wall, st.gpuSeconds,
+                        st.pixelSamples / st.gpuSeconds / 1e6, st.rays / st.gpuSeconds / 1e6,
+                        static_cast<double>(st.rays) / static_cast<double>(st.pixelSamples), st.maxDepth,
+                        options.saveImage ? ", wrote " : "", options.saveImage ? options.outputPath.c_str() : "");
+    } catch (std::exception const &e) {
+        std::fprintf(stderr, "cornelis: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

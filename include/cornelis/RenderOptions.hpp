@@ -1,0 +1,30 @@
+// Render options.  The reference has a single field, samplesAA (include/cornelis/RenderOptions.hpp:6-16); everything
+// else it hard-codes — 512x512 (Render.cpp:307), seed 19791102 (PRNG.hpp:12), no depth limit (Render.cpp:237), the
+// output name (Render.cpp:264).  Those literals are the defaults here, so RenderOptions{} and
+// RenderOptions{samples} behave like the reference.
+#pragma once
+
+#include <cstdint>
+#include <string>
+
+namespace cornelis {
+
+struct RenderOptions {
+    static constexpr std::int32_t DefaultSamplesAA = 1 << 8;
+
+    // Samples per pixel for anti-aliasing — the main quality control (a Monte-Carlo path tracer's noise level).
+    std::int32_t samplesAA = DefaultSamplesAA;
+
+    // ---- extensions (defaults = the reference's literals) ----
+    std::int32_t width = 512;
+    std::int32_t height = 512;
+    std::uint64_t seed = 19791102;
+    std::int32_t maxDepth = 0;       // 0 = unlimited; otherwise a path stops after this many bounces
+    std::int32_t devices = 1;        // GPUs of this box to shard the samples over
+    std::int32_t poolPaths = 0;      // paths in flight per GPU (0 = library default)
+    bool dropNonFinite = false;      // skip NaN/inf path contributions (the reference lets them through)
+    bool saveImage = true;           // write the PNG at the end of render(), as the reference does
+    std::string outputPath = "cornelisrender2.png";
+};
+
+} // namespace cornelis

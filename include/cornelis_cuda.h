@@ -145,6 +145,12 @@ int cornelis_cuda_render_accumulate(cornelis_cuda_scene *scene, const cornelis_r
  * (one all-reduce of n_floats floats).  Valid until the next render with a different frame size or scene destroy. */
 int cornelis_cuda_framebuffer_device(cornelis_cuda_scene *scene, void **device_ptr, size_t *n_floats);
 
+/* Multi-GPU, one process: sum the accumulation buffers of n scenes (one per GPU of this box, same frame size) into
+ * scenes[0].  GPU 0 reads its peers' buffers directly over NVLink (peer access) inside one kernel per peer; without
+ * peer access the buffers are staged through cudaMemcpyPeer.  (bench.py, one process per GPU, uses an NCCL
+ * all-reduce on cornelis_cuda_framebuffer_device() instead.) */
+int cornelis_cuda_reduce_framebuffers(cornelis_cuda_scene *const *scenes, int n);
+
 /* color = sum * (1.0f / samples) (Render.cpp:250) and download: host_rgb[3*W*H]; host_variance[3*W*H] optional
  * (unbiased per-sample variance, only after a CORNELIS_RENDER_VARIANCE render). */
 int cornelis_cuda_resolve(cornelis_cuda_scene *scene, int32_t samples, float *host_rgb, float *host_variance);
