@@ -30,6 +30,27 @@ CB_HD RGBf operator+(RGBf a, RGBf b) { return RGBf{a.r + b.r, a.g + b.g, a.b + b
 
 constexpr float kHemispherePdf = 1.0f / (2.0f * kPi); // randomHemispherePDF(), PRNG.hpp:62
 
+// ---- arithmetic classes -----------------------------------------------------------------------------------------
+// EXACT chain: everything between the random numbers and base = 1 + (alpha^2 - 1) (h.N)^2 — the sampled direction
+// wi, the half vector h, its cosine — uses IEEE division / square root in the reference's operation order.  The GGX
+// term amplifies a 1-ulp change of h.N into ~1e-4 of D for the reference's default roughness, so these values must
+// match the reference to the bit (tests/test_gpu_parity.py checks wi bit for bit).
+// TOLERANT tail: values that are only multiplied into the result (the reciprocal of base^2, Smith G, Fresnel,
+// tan = sin/cos, the Oren-Nayar factor, the final quotients) may be off by a couple of ulp; they use the
+// single-instruction MUFU approximations (<= 2 ulp each), keeping f and pdf within ~3e-6 of the reference against a
+// budget of 1e-5.
+__device__ __forceinline__ float approxSqrt(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float approxRcp(float x) {
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float approxDiv(float a, float b) { return __fdividef(a, b); }
+
 // x^5 for Schlick's (1 - cos)^5 (Materials.cpp:41 uses std::pow(x, 5.0f)): exact-ish in double, rounded once.
 CB_HD float pow5(float x) {
     double d = static_cast<double>(x);
@@ -41,128 +62,131 @@ CB_HD float pow5(float x) {
 CB_HD float schlick(float cosTheta, float r0) { return r0 + (1.0f - r0) * pow5(1.0f - cosTheta); }
 
 // models::distributionGTR2, Materials.cpp:16-26 (std::pow(x, 2.0f) is folded to x*x by the reference's compiler).
-CB_HD float distributionGTR2(float cosThetaH, const DevMaterial &m) {
+// The argument chain up to `base` is exact; the reciprocal is tolerant.
+__device__ __forceinline__ float distributionGTR2(float cosThetaH, const DevMaterial &m) {
     if (isAlmostZero(m.alpha2))
         return 1.0f;
     float c2 = cosThetaH * cosThetaH;
     float base = 1.0f + (m.alpha2 - 1.0f) * c2;
-    float B = 1.0f / (base * base);
-    return m.gtr_a * B;
+    return m.gtr_a * approxRcp(base * base);
 }
 
 // models::lambdaTR, Materials.cpp:28-32.
-CB_HD float lambdaTR(float tanTheta, float alpha) {
+__device__ __forceinline__ float lambdaTR(float tanTheta, float alpha) {
     if (isinf(tanTheta))
         return 0.0f;
     float k = fabsf(tanTheta) * alpha;
-    return (-1.0f + sqrtf(1.0f + k * k)) * 0.5f;
+    return (-1.0f + approxSqrt(1.0f + k * k)) * 0.5f;
 }
 
 // models::shadowMaskingTR, Materials.cpp:34-36.
-CB_HD float shadowMaskingTR(float tanI, float tanO, float alpha) {
-    return 1.0f / (1.0f + lambdaTR(tanI, alpha) + lambdaTR(tanO, alpha));
+__device__ __forceinline__ float shadowMaskingTR(float tanI, float tanO, float alpha) {
+    return approxRcp(1.0f + lambdaTR(tanI, alpha) + lambdaTR(tanO, alpha));
 }
 
-// OrenNayarBRDF::operator(), Materials.hpp:211-228.  Angles come from WORLD-space components (wi.z, wi.x), not
-// relative to N; std::max(0, NaN) == 0 swallows the NaN azimuth of a vertical direction.
+// OrenNayarBRDF::operator(), Materials.hpp:211-228, without its seven transcendental calls.
+//
+// The reference takes the angles from WORLD-space components (cos theta = w.z, cos phi = w.x / sin theta — not
+// relative to N), then evaluates  a + b * max(0, cos(phiI - phiO)) * sin(alpha) * sin(beta)  with
+// phi = acos(r), theta = acos(w.z), alpha/beta = max/min(thetaI, thetaO).  Since acos maps into [0, pi]:
+//   cos(phiI - phiO)         = rI rO + sqrt(1 - rI^2) sqrt(1 - rO^2)
+//   sin(alpha) sin(beta)     = sin(thetaI) sin(thetaO) = sqrt(1 - cI^2) sqrt(1 - cO^2)
+// which differ from the acos/cos/sin route by ~1e-6 absolute, scaled by b (<= 0.33) against a (>= 0.79).
+// NaN behaviour is kept: a NaN azimuth is swallowed by std::max(0, NaN) == 0 in both forms; |wi.z| > 1 makes the
+// factor NaN in both; |wo.z| > 1 alone makes std::max/std::min pick thetaI twice (Materials.hpp:223-224 with a NaN
+// second argument), i.e. sin^2(thetaI).
 __device__ __forceinline__ RGBf orenNayarEval(const DevMaterial &m, V3 wi, V3 wo) {
-    float cosThetaI = wi.z;
-    float cosThetaO = wo.z;
-    float sinThetaI = sqrtf(1.0f - cosThetaI * cosThetaI);
-    float sinThetaO = sqrtf(1.0f - cosThetaO * cosThetaO);
-    float phiI = acosf(wi.x / sinThetaI);
-    float phiO = acosf(wo.x / sinThetaO);
-    float thetaO = acosf(cosThetaO);
-    float thetaI = acosf(cosThetaI);
-    float alpha = stdMax(thetaI, thetaO);
-    float beta = stdMin(thetaI, thetaO);
-    float s = m.on_a + m.on_b * stdMax(0.0f, cosf(phiI - phiO)) * sinf(alpha) * sinf(beta);
+    float cI = wi.z, cO = wo.z;
+    // exact up to r: whether |r| exceeds 1 (-> NaN azimuth -> the b-term vanishes) is a discontinuity of size ~b
+    float sI = sqrtf(1.0f - cI * cI);
+    float sO = sqrtf(1.0f - cO * cO);
+    float rI = wi.x / sI;
+    float rO = wo.x / sO;
+    float cosD = rI * rO + approxSqrt(1.0f - rI * rI) * approxSqrt(1.0f - rO * rO);
+    bool const thetaONaN = !(fabsf(cO) <= 1.0f);
+    float sinProduct = sI * (thetaONaN ? sI : sO);
+    float s = m.on_a + m.on_b * stdMax(0.0f, cosD) * sinProduct;
     return RGBf{m.dr, m.dg, m.db} * s;
 }
 
-// GlossyBRDF::operator(), Materials.hpp:130-154.
-__device__ __forceinline__ RGBf glossyEval(const DevMaterial &m, V3 wi, V3 wo, V3 N) {
-    float cosThetaO = stdMax(0.0f, dot(wo, N));
-    float sinThetaO = sqrtf(1.0f - cosThetaO * cosThetaO);
-    float cosThetaI = stdMax(0.0f, dot(wi, N));
-    float sinThetaI = sqrtf(1.0f - cosThetaI * cosThetaI);
-    if (isAlmostZero(cosThetaO) || isAlmostZero(cosThetaI))
-        return RGBf{0.0f, 0.0f, 0.0f};
-    V3 h = normalize(wi + wo);
+// GlossyBRDF::operator() (Materials.hpp:130-154) and GlossyBRDF::pdf (Materials.hpp:177-188) share the half vector
+// h = normalize(wi + wo), its cosine and D; evaluated together.  Returns the scalar that multiplies the tint.
+__device__ __forceinline__ float glossyEvalPdf(const DevMaterial &m, V3 wi, V3 wo, V3 N, float &pdf) {
+    V3 const h = normalize(wi + wo);                       // exact chain
+    float const cosThetaH = stdMax(0.0f, dot(h, N));
+    float D = 1.0f;
+    if (isAlmostZero(cosThetaH)) {
+        pdf = 1.0f;                                        // Materials.hpp:180-181
+    } else {
+        D = distributionGTR2(cosThetaH, m);
+        float const pdfh = D * fabsf(cosThetaH);
+        float const wiDotH = dot(wi, h);
+        pdf = isAlmostZero(wiDotH) ? pdfh : approxDiv(pdfh, 4.0f * wiDotH);
+    }
+    float const cosThetaO = stdMax(0.0f, dot(wo, N));
+    float const cosThetaI = stdMax(0.0f, dot(wi, N));
+    if (isAlmostZero(cosThetaO) || isAlmostZero(cosThetaI))  // Materials.hpp:141-142
+        return 0.0f;
     if (isAlmostZero(h.x) && isAlmostZero(h.y) && isAlmostZero(h.z))
-        return RGBf{0.0f, 0.0f, 0.0f};
-    float cosThetaH = stdMax(0.0f, dot(h, N));
-    float D = distributionGTR2(cosThetaH, m);
-    float G = shadowMaskingTR(sinThetaI / cosThetaI, sinThetaO / cosThetaO, m.alpha);
-    float F = schlick(cosThetaH, m.r0);
-    return RGBf{m.tr, m.tg, m.tb} * (F * D * G / (4.0f * cosThetaO * cosThetaI));
-}
-
-// GlossyBRDF::pdf, Materials.hpp:177-188.
-__device__ __forceinline__ float glossyPdf(const DevMaterial &m, V3 wi, V3 wo, V3 N) {
-    V3 h = normalize(wi + wo);
-    float cosThetaH = stdMax(0.0f, dot(h, N));
+        return 0.0f;
     if (isAlmostZero(cosThetaH))
-        return 1.0f;
-    float D = distributionGTR2(cosThetaH, m);
-    float pdfh = D * fabsf(cosThetaH);
-    float wiDotH = dot(wi, h);
-    if (isAlmostZero(wiDotH))
-        return pdfh;
-    return pdfh / (4.0f * wiDotH);
+        D = distributionGTR2(cosThetaH, m);                // eval has no shortcut for a grazing half vector
+    float const sinThetaO = approxSqrt(1.0f - cosThetaO * cosThetaO);
+    float const sinThetaI = approxSqrt(1.0f - cosThetaI * cosThetaI);
+    float const G = shadowMaskingTR(approxDiv(sinThetaI, cosThetaI), approxDiv(sinThetaO, cosThetaO), m.alpha);
+    float const F = schlick(cosThetaH, m.r0);
+    return approxDiv(F * D * G, 4.0f * cosThetaO * cosThetaI);
 }
 
-// randomHemisphere(float2, Basis), PRNG.hpp:39-55 — UNIFORM over the hemisphere.
-__device__ __forceinline__ V3 sampleHemisphere(float x1, float x2, const Basis &b) {
-    float a = 2.0f * kPi * x2; // the reference's double product rounds to the same float (exact 48-bit product)
-    float r = sqrtf(1.0f - x1 * x1);
-    double sa, ca;
-    sincos(static_cast<double>(a), &sa, &ca);
-    V3 v{static_cast<float>(ca * static_cast<double>(r)), static_cast<float>(sa * static_cast<double>(r)), x1};
-    return b.B * v.x + b.T * v.y + b.N * v.z;
-}
-
-// GlossyBRDF::generateDirection, Materials.hpp:156-175 — only wi matters to the caller (Materials.hpp:281-289);
-// on the early-out wi keeps the zero it was initialised with (Render.cpp:198).
-__device__ __forceinline__ void sampleGlossy(const DevMaterial &m, V3 wo, float x0, float x1, const Basis &b, V3 &wi) {
-    float A = 1.0f - x1;
-    float B = 1.0f + (m.alpha2 - 1.0f) * x1;
-    float cosThetaH = sqrtf(A / B);
-    float sinThetaH = sqrtf(1.0f - cosThetaH * cosThetaH);
-    float phi = 2.0f * kPi * x0;
-    double sp, cp;
-    sincos(static_cast<double>(phi), &sp, &cp);
-    float const kB = static_cast<float>(static_cast<double>(sinThetaH) * cp);
-    float const kT = static_cast<float>(static_cast<double>(sinThetaH) * sp);
-    V3 h = normalize(kB * b.B + kT * b.T + cosThetaH * b.N);
-    if (dot(h, b.N) < 0.0f)
-        return;
-    wi = normalize((2.0f * dot(wo, h)) * h - wo);
-}
-
-// LayeredBRDF::operator(), Materials.hpp:255-263.
-__device__ __forceinline__ RGBf layeredEval(const DevMaterial &m, V3 wi, V3 wo, V3 N) {
-    RGBf Df = orenNayarEval(m, wi, wo);
-    RGBf Gf = glossyEval(m, wi, wo, N);
-    float k = 1.0f - schlick(stdMax(0.0f, dot(N, wi)), m.r0);
+// LayeredBRDF::operator() and ::pdf (Materials.hpp:255-277): f = (1 - F(N.wi)) * diffuse + glossy;
+// pdf = 0.5 * (1/(2 Pi) + pdf_glossy) — the unweighted average whatever lobe was sampled.
+__device__ __forceinline__ RGBf layeredEvalPdf(const DevMaterial &m, V3 wi, V3 wo, V3 N, float &pdf) {
+    float pdfGlossy;
+    float const g = glossyEvalPdf(m, wi, wo, N, pdfGlossy);
+    pdf = 0.5f * (kHemispherePdf + pdfGlossy);
+    RGBf const Df = orenNayarEval(m, wi, wo);
+    RGBf const Gf = RGBf{m.tr, m.tg, m.tb} * g;
+    float const k = 1.0f - schlick(stdMax(0.0f, dot(N, wi)), m.r0);
     return Df * k + Gf;
 }
 
-// LayeredBRDF::pdf, Materials.hpp:265-277 — the unweighted average whatever lobe was sampled.
-__device__ __forceinline__ float layeredPdf(const DevMaterial &m, V3 wi, V3 wo, V3 N) {
-    return 0.5f * (kHemispherePdf + glossyPdf(m, wi, wo, N));
-}
-
-// LayeredBRDF::generateDirection, Materials.hpp:279-293.  x2 picks the lobe (its rescaled value is unused).
+// LayeredBRDF::generateDirection, Materials.hpp:279-293: x2 < 0.5 samples the diffuse lobe UNIFORMLY over the
+// hemisphere (BRDF::generateDirection -> randomHemisphere, PRNG.hpp:39-55), otherwise the GGX half vector
+// (GlossyBRDF::generateDirection, Materials.hpp:156-175).  Both lobes build
+//     float(cos_d(angle) * radial) * B + float(sin_d(angle) * radial) * T + axial * N
+// with the sine/cosine evaluated in DOUBLE and the double product rounded once — as the reference's unqualified
+// cos()/sin() do — so one sincos serves whichever lobe a lane picked:
+//     diffuse: angle = 2 Pi x1, radial = sqrt(1 - x0^2),         axial = x0
+//     glossy:  angle = 2 Pi x0, radial = sin(theta_h),           axial = cos(theta_h) = sqrt((1-x1)/(1+(a^2-1)x1))
+// The lobe's own f/pdf are discarded by the reference (Materials.hpp:281-289); pdf and f come from the layered
+// functions at the sampled wi.  If the half vector falls below the surface wi stays 0 (Materials.hpp:169-170).
 __device__ __forceinline__ RGBf layeredSample(const DevMaterial &m, V3 wo, float x0, float x1, float x2,
                                               const Basis &b, V3 &wi, float &pdf) {
-    wi = V3{0.0f, 0.0f, 0.0f};
-    if (x2 < 0.5f)
-        wi = sampleHemisphere(x0, x1, b);
-    else
-        sampleGlossy(m, wo, x0, x1, b, wi);
-    pdf = layeredPdf(m, wi, wo, b.N);
-    return layeredEval(m, wi, wo, b.N);
+    bool const diffuse = x2 < 0.5f;
+    float radial, axial;
+    if (diffuse) {
+        radial = sqrtf(1.0f - x0 * x0);
+        axial = x0;
+    } else {
+        float const A = 1.0f - x1;
+        float const B = 1.0f + (m.alpha2 - 1.0f) * x1;
+        axial = sqrtf(A / B);
+        radial = sqrtf(1.0f - axial * axial);
+    }
+    float const angle = 2.0f * kPi * (diffuse ? x1 : x0); // == float(2.0 * Pi * x): the 48-bit product is exact in double
+    double sn, cs;
+    sincos(static_cast<double>(angle), &sn, &cs);
+    float const kB = static_cast<float>(cs * static_cast<double>(radial));
+    float const kT = static_cast<float>(sn * static_cast<double>(radial));
+    V3 const v = (kB * b.B + kT * b.T) + axial * b.N;
+    wi = v;
+    if (!diffuse) {
+        wi = V3{0.0f, 0.0f, 0.0f};
+        V3 const h = normalize(v);
+        if (!(dot(h, b.N) < 0.0f))
+            wi = normalize((2.0f * dot(wo, h)) * h - wo);
+    }
+    return layeredEvalPdf(m, wi, wo, b.N, pdf);
 }
 
 // russianRouletteFactor, Render.cpp:153-165.

@@ -320,9 +320,10 @@ __global__ void __launch_bounds__(kBlockThreads) k_bsdf_eval(const DevMaterial *
         V3 const a{wi[3 * k], wi[3 * k + 1], wi[3 * k + 2]}, o{wo[3 * k], wo[3 * k + 1], wo[3 * k + 2]};
         V3 const nrm{N[3 * k], N[3 * k + 1], N[3 * k + 2]};
         DevMaterial const &m = materials[mat[k]];
-        RGBf const v = layeredEval(m, a, o, nrm);
+        float p;
+        RGBf const v = layeredEvalPdf(m, a, o, nrm, p);
         f[3 * k] = v.r, f[3 * k + 1] = v.g, f[3 * k + 2] = v.b;
-        pdf[k] = layeredPdf(m, a, o, nrm);
+        pdf[k] = p;
     }
 }
 
