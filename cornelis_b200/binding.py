@@ -21,7 +21,7 @@ EXPORTS = [
     "cornelis_cuda_resolve_srgb8",
     "cornelis_cuda_render", "cornelis_cuda_pixel_rays", "cornelis_cuda_intersect",
     "cornelis_cuda_intersect_device", "cornelis_cuda_bsdf_sample", "cornelis_cuda_bsdf_eval",
-    "cornelis_cuda_shade", "cornelis_cuda_rng_uniforms",
+    "cornelis_cuda_shade", "cornelis_cuda_rng_uniforms", "cornelis_cuda_selftest_arith",
 ]
 
 OK, ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_ABORTED = range(6)
@@ -105,6 +105,7 @@ def lib():
         L.cornelis_cuda_bsdf_eval.argtypes = [vp, sz, f, f, f, f, f, f]
         L.cornelis_cuda_shade.argtypes = [vp, sz, i32, f, f, f, f, f, f, f, f, f]
         L.cornelis_cuda_rng_uniforms.argtypes = [vp, C.c_uint64, sz, f, f, f, f]
+        L.cornelis_cuda_selftest_arith.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -310,6 +311,11 @@ class Scene:
         _check(lib().cornelis_cuda_shade(self.handle, n, depth, _ptr(u), _ptr(P), _ptr(N), _ptr(mat), _ptr(org),
                                          _ptr(dirs), _ptr(thr), _ptr(rad), _ptr(alive)))
         return dict(org=org, dir=dirs, thr=thr, rad=rad, alive=alive.astype(bool))
+
+    def selftest_arith(self, mode, n, seed=1):
+        bad = C.c_uint64(0)
+        _check(lib().cornelis_cuda_selftest_arith(self.handle, mode, n, seed, C.byref(bad)))
+        return bad.value
 
     def rng_uniforms(self, seed, pixel, sample, block):
         pixel = np.ascontiguousarray(pixel, np.uint32)

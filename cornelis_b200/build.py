@@ -26,7 +26,7 @@ OBJ = LIB / "obj"
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = [*ARCH, "-lineinfo", "-O3", "--fmad=false", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off",
-              "-Xptxas", "-v"]
+              "-Xptxas", "-v", *os.environ.get("CORNELIS_NVCC_EXTRA", "").split()]
 
 
 def _stale(target: Path, sources) -> bool:

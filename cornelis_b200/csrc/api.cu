@@ -249,9 +249,6 @@ int cornelis_cuda_scene_create(int device, const cornelis_camera_desc *camera, c
     cudaDeviceProp prop{};
     CB_CUDA(cudaGetDeviceProperties(&prop, device));
     s->shape.numSMs = prop.multiProcessorCount;
-    if (const char *env = std::getenv("CORNELIS_BLOCKS_PER_SM"))
-        s->shape.blocksPerSM = std::max(1, std::atoi(env));
-    s->shape.gridPersistent = s->shape.numSMs * s->shape.blocksPerSM;
 
     // SphereData / PlaneData / materials (Scene.cpp:5-53) flattened to the device tables.
     std::vector<DevSphere> hs(n_spheres);
@@ -271,6 +268,18 @@ int cornelis_cuda_scene_create(int device, const cornelis_camera_desc *camera, c
         p.tx = b.T.x, p.ty = b.T.y, p.tz = b.T.z;
         p.material = d.material >= 0 ? static_cast<uint32_t>(d.material) : 0u;
         p.bx = b.B.x, p.by = b.B.y, p.bz = b.B.z;
+        // Axis class for the exact fast path of closestHit: the normal is +-e_k and constructBasis produced the
+        // in-plane axes closestHit assumes (x: T=z, B=y; y: T=x, B=z; z: T=x, B=y), all with unit magnitude.
+        auto unitAxis = [](float x, float y, float z) -> int {
+            if (fabsf(x) == 1.0f && y == 0.0f && z == 0.0f) return 0;
+            if (x == 0.0f && fabsf(y) == 1.0f && z == 0.0f) return 1;
+            if (x == 0.0f && y == 0.0f && fabsf(z) == 1.0f) return 2;
+            return 3;
+        };
+        int const kN = unitAxis(p.nx, p.ny, p.nz), kT = unitAxis(p.tx, p.ty, p.tz), kB = unitAxis(p.bx, p.by, p.bz);
+        bool const expected = (kN == 0 && kT == 2 && kB == 1) || (kN == 1 && kT == 0 && kB == 2) ||
+                              (kN == 2 && kT == 0 && kB == 1);
+        p.pad = expected ? static_cast<uint32_t>(kN) : 3u;
         hp[i] = p;
     }
     std::vector<DevMaterial> hm(n_materials);
@@ -307,7 +316,7 @@ int cornelis_cuda_scene_create(int device, const cornelis_camera_desc *camera, c
                     "scene tables exceed the shared-memory staging limit of this build (" + std::to_string(smem) +
                         " bytes)");
     s->shape.sceneSmemBytes = smem;
-    CB_CUDA(configureKernels(smem));
+    CB_CUDA(configureKernels(s->shape));
 
     guard.p = nullptr;
     *out_scene = s;
@@ -804,6 +813,24 @@ int cornelis_cuda_rng_uniforms(cornelis_cuda_scene *s, uint64_t seed, size_t n, 
     DOWNLOAD(out, s->stageF[0], 4 * n);
     CB_CUDA(cudaStreamSynchronize(s->stream));
     CB_CUDA(cudaGetLastError());
+    return CORNELIS_OK;
+}
+
+int cornelis_cuda_selftest_arith(cornelis_cuda_scene *s, int mode, uint64_t n, uint32_t seed, uint64_t *mismatches) {
+    if (int rc = checkScene(s))
+        return rc;
+    if (!mismatches || (mode != 0 && mode != 1))
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "bad argument");
+    DeviceBuffer<unsigned long long> counter;
+    CB_CUDA(counter.reserve(1));
+    CB_CUDA(cudaMemsetAsync(counter.ptr, 0, sizeof(unsigned long long), s->stream));
+    launchSelftestArith(s->stream, s->shape, mode, n, seed, counter.ptr);
+    unsigned long long host = 0;
+    CB_CUDA(cudaMemcpyAsync(&host, counter.ptr, sizeof host, cudaMemcpyDeviceToHost, s->stream));
+    CB_CUDA(cudaStreamSynchronize(s->stream));
+    CB_CUDA(cudaGetLastError());
+    counter.release();
+    *mismatches = host;
     return CORNELIS_OK;
 }
 

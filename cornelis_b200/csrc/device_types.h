@@ -21,7 +21,7 @@ struct DevPlane {    // 4 x float4
     float px, py, pz, width;   // point on the plane; extents[0] (Scene.cpp:28-33)
     float nx, ny, nz, height;  // normal;             extents[1]
     float tx, ty, tz; uint32_t material; // constructBasis(normal).T (Math.hpp:424-434), hoisted out of Geometry.cpp:165
-    float bx, by, bz; uint32_t pad;      // constructBasis(normal).B
+    float bx, by, bz; uint32_t pad;      // constructBasis(normal).B; pad = axis class: 0/1/2 normal = +-x/y/z, 3 general
 };
 
 struct DevMaterial { // 4 x float4 — StandardMaterial (Materials.hpp:325-338) with its constants folded

@@ -2,6 +2,8 @@
 #include "kernels.cuh"
 #include "wavefront.h"
 
+#include <cstdlib>
+
 namespace cornelis_b200 {
 
 // ---------------------------------------------------------------------------------------------------- plan --
@@ -59,7 +61,10 @@ __global__ void __launch_bounds__(kBlockThreads) k_raygen(const Control *ctl, Re
 // intersect (Render.cpp:110-150): closest hit of every pooled ray against all spheres then all planes held in
 // shared memory, then compaction #1: hits are appended to the hit queue; misses end the path — if it carries
 // radiance it goes to the finished queue, otherwise it simply disappears.
-__global__ void __launch_bounds__(kBlockThreads) k_intersect(Control *ctl, SceneView scene, PathPool pool,
+#ifndef CORNELIS_INTERSECT_MIN_BLOCKS
+#define CORNELIS_INTERSECT_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(kBlockThreads, CORNELIS_INTERSECT_MIN_BLOCKS) k_intersect(Control *ctl, SceneView scene, PathPool pool,
                                                              HitRecord *__restrict__ hits,
                                                              uint32_t *__restrict__ hitQueue,
                                                              FinishedPath *__restrict__ finished) {
@@ -72,12 +77,16 @@ __global__ void __launch_bounds__(kBlockThreads) k_intersect(Control *ctl, Scene
         bool const valid = i < n;
         bool hit = false, finish = false;
         float4 radiance = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = o4;
         if (valid) {
-            float4 const o4 = pool.org[i], d4 = pool.dir[i];
-            float t = INFINITY; // IntersectionData::reset, Geometry.cpp:7-12
-            int32_t prim = -1;
-            closestHit(V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, sh.spheres, scene.nSpheres, sh.planes,
-                       scene.nPlanes, t, prim);
+            o4 = pool.org[i];
+            d4 = pool.dir[i];
+        }
+        float t = INFINITY; // IntersectionData::reset, Geometry.cpp:7-12
+        int32_t prim = -1;
+        closestHit(valid, V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, sh.spheres, scene.nSpheres, sh.planes,
+                   scene.nPlanes, t, prim);
+        if (valid) {
             hit = t < INFINITY; // Render.cpp:146
             hits[i] = HitRecord{t, prim};
             if (!hit) {
@@ -98,7 +107,10 @@ __global__ void __launch_bounds__(kBlockThreads) k_intersect(Control *ctl, Scene
 // accumulateAndBounce (Render.cpp:167-218) over the hit queue, then compaction #2: survivors are written
 // CONTIGUOUSLY into the next pool (so the next pass reads coalesced float4 streams); paths killed by Russian
 // roulette or the depth cap go to the finished queue if they carry radiance.
-__global__ void __launch_bounds__(kBlockThreads) k_shade(Control *ctl, RenderConfig cfg, SceneView scene,
+#ifndef CORNELIS_SHADE_MIN_BLOCKS
+#define CORNELIS_SHADE_MIN_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(kBlockThreads, CORNELIS_SHADE_MIN_BLOCKS) k_shade(Control *ctl, RenderConfig cfg, SceneView scene,
                                                          PathPool in, PathPool out,
                                                          const HitRecord *__restrict__ hits,
                                                          const uint32_t *__restrict__ hitQueue,
@@ -260,14 +272,21 @@ __global__ void __launch_bounds__(kBlockThreads) k_intersect_batch(SceneView sce
                                                                    HitRecord *__restrict__ hits) {
     extern __shared__ __align__(16) unsigned char smem[];
     SharedScene const sh = stageScene(scene, smem, false);
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        float4 const o4 = org[i], d4 = dir[i];
+    for (size_t base = static_cast<size_t>(blockIdx.x) * blockDim.x; base < n;
+         base += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        size_t const i = base + threadIdx.x;
+        bool const valid = i < n;
+        float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = o4;
+        if (valid) {
+            o4 = org[i];
+            d4 = dir[i];
+        }
         float t = INFINITY;
         int32_t prim = -1;
-        closestHit(V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, sh.spheres, scene.nSpheres, sh.planes, scene.nPlanes, t,
-                   prim);
-        hits[i] = HitRecord{t, prim};
+        closestHit(valid, V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, sh.spheres, scene.nSpheres, sh.planes,
+                   scene.nPlanes, t, prim);
+        if (valid)
+            hits[i] = HitRecord{t, prim};
     }
 }
 
@@ -354,6 +373,40 @@ __global__ void __launch_bounds__(kBlockThreads) k_rng(uint32_t n, uint32_t key0
     }
 }
 
+// Self-test of the exact fast paths of geometry.cuh against the IEEE operators: operands with random sign and
+// mantissa (one in eight with an all-ones / all-zeros / single-bit mantissa) and exponents spanning the ranges the fast
+// paths claim.  mode 0: division, mode 1: square root.  Counts results whose bits differ.
+__global__ void __launch_bounds__(kBlockThreads) k_selftest_arith(int mode, unsigned long long n, uint32_t seed,
+                                                                  unsigned long long *mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+        Philox4 const r = philox4x32_10(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), 0x5e1f7e57u, 0u, seed, 0u);
+        auto craft = [](uint32_t bits, uint32_t style, int eLo, int eHi) {
+            uint32_t mant = bits & 0x7fffffu;
+            switch (style & 7u) {
+            case 0: mant = 0x7fffffu; break;
+            case 1: mant = 0u; break;
+            case 2: mant = 1u << ((bits >> 3) % 23u); break;
+            case 3: mant = 0x7fffffu ^ (1u << ((bits >> 3) % 23u)); break;
+            default: break;
+            }
+            int const e = eLo + static_cast<int>((bits >> 23) % static_cast<uint32_t>(eHi - eLo + 1));
+            return __uint_as_float((bits & 0x80000000u) | (static_cast<uint32_t>(e + 127) << 23) | mant);
+        };
+        if (mode == 0) {
+            float const a = craft(r.v[0], r.v[2], -80, 79), b = craft(r.v[1], r.v[2] >> 3, -40, 39);
+            float const fast = divideExactFast(a, b, rcpSeedRefined(b));
+            bad += __float_as_uint(fast) != __float_as_uint(a / b);
+        } else {
+            float const x = fabsf(craft(r.v[0], r.v[2], -100, 125));
+            bad += __float_as_uint(sqrtExactFast(x)) != __float_as_uint(sqrtf(x));
+        }
+    }
+    if (bad)
+        atomicAdd(mismatches, bad);
+}
+
 // Packed xyz -> float4 staging for the host-buffer stage entry points.
 __global__ void __launch_bounds__(kBlockThreads) k_pack4(size_t n, const float *xyz, float4 *out) {
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -383,25 +436,25 @@ void launchPlan(cudaStream_t s, Control *ctl, const RenderConfig &cfg) { k_plan<
 
 void launchRaygen(cudaStream_t s, const LaunchShape &shape, const Control *ctl, const RenderConfig &cfg,
                   const DevCamera &cam, const PathPool &pool) {
-    k_raygen<<<shape.gridPersistent, kBlockThreads, 0, s>>>(ctl, cfg, cam, pool);
+    k_raygen<<<shape.gridRaygen, kBlockThreads, 0, s>>>(ctl, cfg, cam, pool);
 }
 
 void launchIntersect(cudaStream_t s, const LaunchShape &shape, Control *ctl, const SceneView &scene,
                      const PathPool &pool, HitRecord *hits, uint32_t *hitQueue, FinishedPath *finished) {
-    k_intersect<<<shape.gridPersistent, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, scene, pool, hits, hitQueue,
+    k_intersect<<<shape.gridIntersect, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, scene, pool, hits, hitQueue,
                                                                                  finished);
 }
 
 void launchShade(cudaStream_t s, const LaunchShape &shape, Control *ctl, const RenderConfig &cfg,
                  const SceneView &scene, const PathPool &in, const PathPool &out, const HitRecord *hits,
                  const uint32_t *hitQueue, FinishedPath *finished) {
-    k_shade<<<shape.gridPersistent, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, cfg, scene, in, out, hits, hitQueue,
+    k_shade<<<shape.gridShade, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, cfg, scene, in, out, hits, hitQueue,
                                                                              finished);
 }
 
 void launchAccumulate(cudaStream_t s, const LaunchShape &shape, const Control *ctl, const FinishedPath *finished,
                       float4 *accum, float4 *accum2, bool dropNonFinite) {
-    k_accumulate<<<shape.gridPersistent, kBlockThreads, 0, s>>>(ctl, finished, accum, accum2, dropNonFinite);
+    k_accumulate<<<shape.gridAccumulate, kBlockThreads, 0, s>>>(ctl, finished, accum, accum2, dropNonFinite);
 }
 
 void launchResolve(cudaStream_t s, const LaunchShape &shape, uint32_t npixels, uint32_t samples, const float4 *accum,
@@ -462,6 +515,11 @@ void launchRng(cudaStream_t s, const LaunchShape &shape, uint32_t n, uint32_t ke
     k_rng<<<gridFor(n, shape.numSMs, 8), kBlockThreads, 0, s>>>(n, key0, key1, pixel, sample, block, out);
 }
 
+void launchSelftestArith(cudaStream_t s, const LaunchShape &shape, int mode, unsigned long long n, uint32_t seed,
+                          unsigned long long *mismatches) {
+    k_selftest_arith<<<shape.numSMs * 8, kBlockThreads, 0, s>>>(mode, n, seed, mismatches);
+}
+
 void launchPack4(cudaStream_t s, const LaunchShape &shape, size_t n, const float *xyz, float4 *out) {
     k_pack4<<<gridFor(n, shape.numSMs, 8), kBlockThreads, 0, s>>>(n, xyz, out);
 }
@@ -471,19 +529,38 @@ void launchUnpackHits(cudaStream_t s, const LaunchShape &shape, size_t n, const 
     k_unpack_hits<<<gridFor(n, shape.numSMs, 8), kBlockThreads, 0, s>>>(n, hits, t, prim);
 }
 
-cudaError_t configureKernels(size_t sceneSmemBytes) {
-    // Scenes whose tables exceed the default 48 KB of dynamic shared memory opt in to the large carve-out.
-    if (sceneSmemBytes <= 48 * 1024)
-        return cudaSuccess;
+cudaError_t configureKernels(LaunchShape &shape) {
     cudaError_t e;
-    int const bytes = static_cast<int>(sceneSmemBytes);
-    if ((e = cudaFuncSetAttribute(k_intersect, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
+    int const bytes = static_cast<int>(shape.sceneSmemBytes);
+    // Scenes whose tables exceed the default 48 KB of dynamic shared memory opt in to the large carve-out.
+    if (shape.sceneSmemBytes > 48 * 1024) {
+        if ((e = cudaFuncSetAttribute(k_intersect, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
+            return e;
+        if ((e = cudaFuncSetAttribute(k_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
+            return e;
+        if ((e = cudaFuncSetAttribute(k_intersect_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
+            return e;
+        if ((e = cudaFuncSetAttribute(k_hit_surface, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
+            return e;
+    }
+    auto resident = [&](auto kernel, size_t smem, int &grid) -> cudaError_t {
+        int blocks = 0;
+        cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, kBlockThreads, smem);
+        if (err != cudaSuccess)
+            return err;
+        if (const char *env = std::getenv("CORNELIS_BLOCKS_PER_SM"))
+            if (std::atoi(env) > 0)
+                blocks = std::atoi(env);
+        grid = shape.numSMs * (blocks > 0 ? blocks : 1);
+        return cudaSuccess;
+    };
+    if ((e = resident(k_raygen, 0, shape.gridRaygen)) != cudaSuccess)
         return e;
-    if ((e = cudaFuncSetAttribute(k_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
+    if ((e = resident(k_intersect, shape.sceneSmemBytes, shape.gridIntersect)) != cudaSuccess)
         return e;
-    if ((e = cudaFuncSetAttribute(k_intersect_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
+    if ((e = resident(k_shade, shape.sceneSmemBytes, shape.gridShade)) != cudaSuccess)
         return e;
-    return cudaFuncSetAttribute(k_hit_surface, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return resident(k_accumulate, 0, shape.gridAccumulate);
 }
 
 } // namespace cornelis_b200

@@ -11,12 +11,15 @@ namespace cornelis_b200 {
 
 struct LaunchShape {
     int numSMs = 148;         // B200: 148 SMs; queried at scene creation
-    int blocksPerSM = 4;      // resident 256-thread CTAs per SM the persistent kernels are sized for
-    int gridPersistent = 592; // numSMs * blocksPerSM
+    int blocksPerSM = 4;      // resident 256-thread CTAs per SM for the stage entry points
+    // Persistent grids: numSMs x (CTAs of that kernel resident per SM, from the occupancy calculator), so every CTA
+    // is resident for the whole launch and the grid-stride loops split the pool evenly.
+    int gridRaygen = 592, gridIntersect = 592, gridShade = 592, gridAccumulate = 592;
     size_t sceneSmemBytes = 0;
 };
 
-cudaError_t configureKernels(size_t sceneSmemBytes);
+// Opts the kernels in to the scene's shared-memory size and fills the persistent grid sizes.
+cudaError_t configureKernels(LaunchShape &shape);
 
 void launchPlan(cudaStream_t s, Control *ctl, const RenderConfig &cfg);
 void launchRaygen(cudaStream_t s, const LaunchShape &shape, const Control *ctl, const RenderConfig &cfg,
@@ -52,6 +55,8 @@ void launchShadeExplicit(cudaStream_t s, const LaunchShape &shape, const DevMate
                          float *org, float *dir, float *thr, float *rad, uint8_t *alive);
 void launchRng(cudaStream_t s, const LaunchShape &shape, uint32_t n, uint32_t key0, uint32_t key1,
                const uint32_t *pixel, const uint32_t *sample, const uint32_t *block, float *out);
+void launchSelftestArith(cudaStream_t s, const LaunchShape &shape, int mode, unsigned long long n, uint32_t seed,
+                          unsigned long long *mismatches);
 void launchPack4(cudaStream_t s, const LaunchShape &shape, size_t n, const float *xyz, float4 *out);
 void launchUnpackHits(cudaStream_t s, const LaunchShape &shape, size_t n, const HitRecord *hits, float *t,
                       int32_t *prim);

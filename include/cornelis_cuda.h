@@ -201,6 +201,10 @@ int cornelis_cuda_shade(cornelis_cuda_scene *scene, size_t n, int32_t depth, con
 int cornelis_cuda_rng_uniforms(cornelis_cuda_scene *scene, uint64_t seed, size_t n, const uint32_t *pixel,
                                const uint32_t *sample, const uint32_t *block, float *out);
 
+/* Device self-test of the exact fast division (mode 0) / square root (mode 1) used by the intersection kernel against
+ * the IEEE operators on n crafted operand pairs; *mismatches receives the number of results whose bits differ. */
+int cornelis_cuda_selftest_arith(cornelis_cuda_scene *scene, int mode, uint64_t n, uint32_t seed, uint64_t *mismatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -124,6 +124,49 @@ def test_intersect_full_size_properties(binding, oracle):
     assert 0.2 < sph.mean() < 0.35
 
 
+def test_exact_fast_paths(binding):
+    """The hand-scheduled division / square root of the intersection kernel equal the IEEE operators bit for bit on
+    2^28 crafted operands each (random and all-ones / all-zeros / single-bit mantissas over the claimed exponent ranges)."""
+    sc = binding.Scene(scenes.cornell_box())
+    assert sc.selftest_arith(0, 1 << 28, seed=7) == 0
+    assert sc.selftest_arith(1, 1 << 28, seed=9) == 0
+
+
+def test_general_planes_and_odd_rays(binding, oracle):
+    """Tilted planes take the general path, axis-aligned ones the exact fast path; rays with zero components, on-plane
+    origins, huge / tiny / non-finite components must all agree with the oracle bit for bit."""
+    flat = scenes.cornell_box()
+    n1 = np.array([1, 1, 0], np.float32) / np.sqrt(np.float32(2))
+    n2 = np.array([0.3, -0.5, 0.81], np.float32)
+    n2 = n2 / np.float32(np.linalg.norm(n2))
+    flat["planes"] = np.concatenate([flat["planes"], [[*n1, 50, 200, 0, 300, 300, 0], [*n2, -100, 300, 100, 250, 400, 0]]]
+                                    ).astype(np.float32)
+    flat["plane_mat"] = np.concatenate([flat["plane_mat"], [1, 2]]).astype(np.int32)
+    sc, osc = binding.Scene(flat), oracle.scene(flat)
+    rng = np.random.default_rng(77)
+    n = 200000
+    o = (rng.random((n, 3), dtype=np.float32) * 560 - np.float32([280, 0, 280])).astype(np.float32)
+    d = unit(rng, n)
+    k = np.arange(n)
+    d[k % 11 == 0, 0] = 0                      # axis-parallel directions (parallel to walls)
+    d[k % 13 == 0, 1] = 0
+    d[k % 17 == 0, 2] = 0
+    o[k % 19 == 0, 1] = 0                      # origins exactly on the floor plane
+    o[k % 23 == 0, 0] = np.float32(-275)       # ... on the left wall
+    o[k % 29 == 0] = np.float32([0, 0, 0])     # the floor's own point: diff == 0
+    d[k % 31 == 0] *= np.float32(1e-3)
+    d[k % 37 == 0] *= np.float32(1e6)          # beyond the fast-path range
+    o[k % 41 == 0] *= np.float32(1e8)
+    d[k % 43 == 0, 0] = np.float32(np.inf)
+    o[k % 47 == 0, 2] = np.float32(np.nan)
+    d[k % 53 == 0] = np.float32(3e-5)          # degenerate direction
+    o[k % 59 == 0] *= np.float32(1e-30)
+    a, b = sc.intersect(o, d), osc.intersect(o, d)
+    assert np.array_equal(a["prim"], b["prim"])
+    assert ulp_distance(a["t"], b["t"]).max() == 0 and np.array_equal(np.isnan(a["t"]), np.isnan(b["t"]))
+    assert (a["prim"] >= 9).any() and (a["prim"] == 3).any()
+
+
 # ---------------------------------------------------------------------------------------------------- materials --
 
 def _bsdf_inputs(rng, n, n_mat):
