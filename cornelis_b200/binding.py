@@ -26,7 +26,7 @@ EXPORTS = [
 
 OK, ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_ABORTED = range(6)
 RENDER_VARIANCE, RENDER_KEEP, RENDER_STAGE_TIMING, RENDER_DROP_NONFINITE = 1, 2, 4, 8
-PIPELINE_DEFAULT, PIPELINE_WAVEFRONT = 0, 1
+PIPELINE_DEFAULT, PIPELINE_WAVEFRONT, PIPELINE_PERSISTENT = 0, 1, 2
 DEFAULT_SEED = 19791102
 
 

@@ -1,4 +1,5 @@
 // C-ABI of the render path (include/cornelis_cuda.h): scene upload, wavefront driver, stage entry points.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -105,6 +106,8 @@ struct cornelis_cuda_scene {
     DeviceBuffer<uint32_t> hitQueue;
     DeviceBuffer<FinishedPath> finished;
     DeviceBuffer<Control> control;
+    DeviceBuffer<unsigned long long> claimCursor; // persistent pipeline: next camera path to claim
+    int gridPersistent = 0;
     Control *hostControl = nullptr; // pinned
     DeviceBuffer<float4> accum, accum2;
     bool haveVariance = false;
@@ -126,7 +129,7 @@ struct cornelis_cuda_scene {
         for (auto &half : pool)
             for (auto &b : half)
                 b.release();
-        hits.release(), hitQueue.release(), finished.release(), control.release();
+        hits.release(), hitQueue.release(), finished.release(), control.release(), claimCursor.release();
         accum.release(), accum2.release(), outRgb.release(), outVar.release(), outRgb8.release();
         for (auto &b : stageF)
             b.release();
@@ -157,13 +160,16 @@ PathPool poolView(cornelis_cuda_scene *s, int which) {
 
 int ensureFrame(cornelis_cuda_scene *s, uint32_t width, uint32_t height, uint32_t poolPaths, bool variance) {
     size_t const npix = static_cast<size_t>(width) * height;
-    for (int half = 0; half < 2; half++)
-        for (int a = 0; a < 4; a++)
-            CB_CUDA(s->pool[half][a].reserve(poolPaths));
-    CB_CUDA(s->hits.reserve(poolPaths));
-    CB_CUDA(s->hitQueue.reserve(poolPaths));
-    CB_CUDA(s->finished.reserve(2 * static_cast<size_t>(poolPaths)));
+    if (poolPaths) { // the wavefront pipeline's path pool and queues
+        for (int half = 0; half < 2; half++)
+            for (int a = 0; a < 4; a++)
+                CB_CUDA(s->pool[half][a].reserve(poolPaths));
+        CB_CUDA(s->hits.reserve(poolPaths));
+        CB_CUDA(s->hitQueue.reserve(poolPaths));
+        CB_CUDA(s->finished.reserve(2 * static_cast<size_t>(poolPaths)));
+    }
     CB_CUDA(s->control.reserve(1));
+    CB_CUDA(s->claimCursor.reserve(1));
     if (!s->hostControl)
         CB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&s->hostControl), sizeof(Control)));
     bool const resized = s->width != width || s->height != height;
@@ -317,6 +323,7 @@ int cornelis_cuda_scene_create(int device, const cornelis_camera_desc *camera, c
                         " bytes)");
     s->shape.sceneSmemBytes = smem;
     CB_CUDA(configureKernels(s->shape));
+    CB_CUDA(configurePersistent(s->shape, s->gridPersistent));
 
     guard.p = nullptr;
     *out_scene = s;
@@ -353,6 +360,17 @@ int cornelis_cuda_render_accumulate(cornelis_cuda_scene *s, const cornelis_rende
     if (npix64 > (1ull << 31))
         return fail(CORNELIS_ERR_INVALID_ARGUMENT, "frame too large");
 
+    int pipeline = p->pipeline;
+    if (pipeline == CORNELIS_PIPELINE_DEFAULT) {
+        pipeline = CORNELIS_PIPELINE_PERSISTENT;
+        if (const char *env = std::getenv("CORNELIS_PIPELINE"))
+            if (std::strcmp(env, "wavefront") == 0)
+                pipeline = CORNELIS_PIPELINE_WAVEFRONT;
+    }
+    if (pipeline != CORNELIS_PIPELINE_WAVEFRONT && pipeline != CORNELIS_PIPELINE_PERSISTENT)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "unknown pipeline");
+    bool const persistent = pipeline == CORNELIS_PIPELINE_PERSISTENT;
+
     uint32_t pool = p->pool_paths > 0 ? static_cast<uint32_t>(p->pool_paths) : (1u << 22);
     if (const char *env = std::getenv("CORNELIS_POOL_PATHS"))
         if (p->pool_paths <= 0 && std::atoll(env) > 0)
@@ -362,7 +380,8 @@ int cornelis_cuda_render_accumulate(cornelis_cuda_scene *s, const cornelis_rende
         pool = static_cast<uint32_t>(total);
     pool = (pool + 255u) & ~255u;
     bool const variance = (p->flags & CORNELIS_RENDER_VARIANCE) != 0;
-    if (int rc = ensureFrame(s, static_cast<uint32_t>(p->width), static_cast<uint32_t>(p->height), pool, variance))
+    if (int rc = ensureFrame(s, static_cast<uint32_t>(p->width), static_cast<uint32_t>(p->height), persistent ? 0u : pool,
+                             variance))
         return rc;
 
     cudaStream_t st = s->stream;
@@ -405,7 +424,30 @@ int cornelis_cuda_render_accumulate(cornelis_cuda_scene *s, const cornelis_rende
     uint64_t pass = 0;
     int const passesPerBatch = 16;
     bool aborted = false;
-    for (;;) {
+    if (persistent) {
+        // One launch renders a slice of the camera-path range; between slices the host reports progress and may abort.
+        bool const drop = (p->flags & CORNELIS_RENDER_DROP_NONFINITE) != 0;
+        uint64_t const slice = std::max<uint64_t>(total / 32 + 1, 1ull << 22);
+        uint64_t done = 0;
+        while (done < total) {
+            uint64_t const limit = std::min(total, done + slice);
+            unsigned long long const start = done;
+            CB_CUDA(cudaMemcpyAsync(s->claimCursor.ptr, &start, sizeof start, cudaMemcpyHostToDevice, st));
+            launchPersistent(st, s->shape, s->gridPersistent, cfg, s->view, s->claimCursor.ptr, limit, s->accum.ptr,
+                             variance ? s->accum2.ptr : nullptr, drop, s->control.ptr);
+            launches += 1;
+            CB_CUDA(cudaStreamSynchronize(st));
+            done = limit;
+            if (done < total && progress && progress(progressUser, done, total) != 0) {
+                aborted = true;
+                break;
+            }
+        }
+        CB_CUDA(cudaMemcpyAsync(s->hostControl, s->control.ptr, sizeof(Control), cudaMemcpyDeviceToHost, st));
+        CB_CUDA(cudaStreamSynchronize(st));
+        s->hostControl->iterations = launches;
+    }
+    for (; !persistent;) {
         for (int k = 0; k < passesPerBatch; k++, pass++) {
             PathPool const in = poolView(s, cur), out = poolView(s, cur ^ 1);
             bool const timed = profileStages && (pass % profileEvery == profileEvery - 1);

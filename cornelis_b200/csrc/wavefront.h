@@ -21,6 +21,12 @@ struct LaunchShape {
 // Opts the kernels in to the scene's shared-memory size and fills the persistent grid sizes.
 cudaError_t configureKernels(LaunchShape &shape);
 
+// persistent-thread pipeline (persistent.cu)
+cudaError_t configurePersistent(LaunchShape &shape, int &grid);
+void launchPersistent(cudaStream_t s, const LaunchShape &shape, int grid, const RenderConfig &cfg, const SceneView &scene,
+                      unsigned long long *cursor, unsigned long long limit, float4 *accum, float4 *accum2,
+                      bool dropNonFinite, Control *ctl);
+
 void launchPlan(cudaStream_t s, Control *ctl, const RenderConfig &cfg);
 void launchRaygen(cudaStream_t s, const LaunchShape &shape, const Control *ctl, const RenderConfig &cfg,
                   const DevCamera &cam, const PathPool &pool);

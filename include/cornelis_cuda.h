@@ -80,7 +80,10 @@ enum {
 
 enum {
     CORNELIS_PIPELINE_DEFAULT = 0,
-    CORNELIS_PIPELINE_WAVEFRONT = 1 /* raygen -> intersect(+compact) -> shade(+compact) -> accumulate kernels */
+    CORNELIS_PIPELINE_WAVEFRONT = 1, /* raygen -> intersect(+compact) -> shade(+compact) -> accumulate kernels over
+                                        a path pool in HBM; works for any scene size */
+    CORNELIS_PIPELINE_PERSISTENT = 2 /* the same stage functions with each path held in its thread's registers and
+                                        finished lanes refilled by a warp-level claim; the default */
 };
 
 typedef struct cornelis_render_params {

@@ -285,13 +285,17 @@ def _three_sigma(mu_g, var_g, n_g, mu_r, var_r, n_r):
     return ok, diff, sigma
 
 
-def test_converged_image_within_three_sigma(binding, golden):
+PIPELINES = [("wavefront", 1), ("persistent", 2)]
+
+
+@pytest.mark.parametrize("pipeline", [p[1] for p in PIPELINES], ids=[p[0] for p in PIPELINES])
+def test_converged_image_within_three_sigma(binding, golden, pipeline):
     """Cornell box 128x128: GPU 4096 spp against the reference's own 4096 spp render (mean + per-sample variance from
     the compiled reference, tests/golden/make_golden.py)."""
     g = golden("render_cornell_128x128_4096spp.npz")
     sc = binding.Scene(scenes.cornell_box())
     spp = 4096
-    st = sc.render_accumulate(128, 128, spp, variance=True)
+    st = sc.render_accumulate(128, 128, spp, variance=True, pipeline=pipeline)
     mean, var = sc.resolve(spp, variance=True)
     ok, diff, sigma = _three_sigma(mean, var, spp, g["mean"], g["variance"], int(g["spp"]))
     # The reference's Oren-Nayar term turns NaN when |w.z| rounds above 1 (about once per 1e8 samples, see
@@ -317,35 +321,42 @@ def test_converged_image_within_three_sigma(binding, golden):
     assert st["pixel_samples"] == 128 * 128 * spp and 8 <= st["max_depth"] <= 40
 
 
-def test_render_against_oracle_other_scene(binding, oracle):
+@pytest.mark.parametrize("pipeline", [p[1] for p in PIPELINES], ids=[p[0] for p in PIPELINES])
+def test_render_against_oracle_other_scene(binding, oracle, pipeline):
     """A second scene (mixed materials, many-sphere style) at a frame that is not a multiple of anything."""
     flat = scenes.many_spheres(60, 12, aspect=0.6)
     W, H, spp_ref, spp = 50, 30, 1024, 2048
     ref = oracle.scene(flat).render(W, H, spp_ref, tile=(10, 10), variance=True, stats=True)
     sc = binding.Scene(flat)
-    st = sc.render_accumulate(W, H, spp, variance=True)
+    st = sc.render_accumulate(W, H, spp, variance=True, pipeline=pipeline)
     mean, var = sc.resolve(spp, variance=True)
     ok, diff, sigma = _three_sigma(mean, var, spp, ref["mean"], ref["variance"], spp_ref)
     assert ok.mean() >= 0.985, ok.mean()
-    sc.render_accumulate(W, H, 256, drop_nonfinite=True)
+    sc.render_accumulate(W, H, 256, drop_nonfinite=True, pipeline=pipeline)
     assert np.isfinite(sc.resolve(256)).all()
     assert abs(st["rays"] / st["pixel_samples"] - ref["stats"]["rays"] / ref["stats"]["pixel_samples"]) < 0.03
 
 
 def test_sample_sharding_and_determinism(binding):
     """Sample ranges add up: [0,32) + [32,64) accumulated == [0,64) (same sample set; fp32 sums differ only by
-    atomic ordering), and the image does not depend on the pool size."""
+    atomic ordering); the image depends neither on the pool size nor on the pipeline: both pipelines trace the SAME
+    paths (identity and random numbers are keyed by pixel, sample, depth)."""
     sc = binding.Scene(scenes.cornell_box())
     W = H = 96
-    sc.render_accumulate(W, H, 64)
+    st_w = sc.render_accumulate(W, H, 64, pipeline=1)
     whole = sc.resolve(64).copy()
-    sc.render_accumulate(W, H, 64, first_sample=0, sample_count=32)
-    sc.render_accumulate(W, H, 64, first_sample=32, sample_count=32, keep=True)
-    parts = sc.resolve(64)
-    assert np.allclose(whole, parts, rtol=1e-5, atol=1e-6)
-    sc.render_accumulate(W, H, 64, pool_paths=4096)
+    for pipeline in (1, 2):
+        sc.render_accumulate(W, H, 64, first_sample=0, sample_count=32, pipeline=pipeline)
+        sc.render_accumulate(W, H, 64, first_sample=32, sample_count=32, keep=True, pipeline=pipeline)
+        parts = sc.resolve(64)
+        assert np.allclose(whole, parts, rtol=1e-5, atol=1e-6)
+    sc.render_accumulate(W, H, 64, pool_paths=4096, pipeline=1)
     small_pool = sc.resolve(64)
     assert np.allclose(whole, small_pool, rtol=1e-5, atol=1e-6)
+    st_p = sc.render_accumulate(W, H, 64, pipeline=2)
+    assert np.allclose(whole, sc.resolve(64), rtol=1e-5, atol=1e-6)
+    for key in ("pixel_samples", "rays", "shaded_hits", "max_depth"):
+        assert st_w[key] == st_p[key], key
     other_seed, _ = sc.render(W, H, 64, seed=12345)
     assert not np.allclose(whole, other_seed, rtol=1e-3, atol=1e-4)
 
