@@ -49,7 +49,8 @@ def parse_args():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--spp", type=int, default=4096)
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak")
-    ap.add_argument("--pool", type=int, default=0, help="paths in flight per GPU (0 = library default)")
+    ap.add_argument("--pool", type=int, default=0, help="paths in flight per GPU (wavefront pipeline; 0 = default)")
+    ap.add_argument("--pipeline", choices=["default", "wavefront", "persistent"], default="default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
@@ -183,7 +184,9 @@ def workload_config(args, note=None):
                      f"(BASELINE.json configs[1])"),
         "width": args.width, "height": args.height, "spp": args.spp,
         "sharding": "sample ranges per GPU + one NCCL sum of the float4 framebuffers",
-        "l2": "path pool + queues (>=600 MB) exceed the 126 MB L2: every pass streams from HBM",
+        "l2": "no L2 flush needed: the persistent pipeline keeps path state in registers (the only global traffic is "
+              "scattered framebuffer atomics over a 33 MB image); the wavefront pipeline's pool + queues (>= 600 MB) "
+              "exceed the 126 MB L2",
         "seed": 19791102,
     }
     if note:
@@ -198,46 +201,60 @@ class DeviceArray:
         self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
 
-def roofline(stats_list, hbm_peak, hbm_source, npixels):
-    """Roofline of the dominant kernel (largest mean launch duration among the sampled stage timings)."""
-    tot = {k: sum(s[k] for s in stats_list) for k in ("rays", "pixel_samples", "shaded_hits", "iterations")}
-    launches = max(1, tot["iterations"])
-    ms = {k: statistics.mean(s[k] for s in stats_list) for k in ("intersect_ms", "shade_ms", "raygen_ms", "accumulate_ms")}
+def roofline(stats_list, hbm_peak, hbm_source, persistent):
+    """Roofline of the dominant kernel.  Algorithmic work per SURVEY.md 8d: 279 flop per ray (4 sphere + 5 plane
+    tests), 250 flop per surviving bounce, 12 per Russian-roulette-killed hit; duration = that kernel's mean launch
+    duration measured with CUDA events inside the timed region."""
+    tot = {k: sum(s[k] for s in stats_list) for k in ("rays", "pixel_samples", "shaded_hits", "iterations",
+                                                       "kernel_launches", "contributions")}
     surviving = tot["rays"] - tot["pixel_samples"]          # every ray after the camera ray came from a surviving bounce
     killed = tot["shaded_hits"] - surviving
-    rays_per_launch = tot["rays"] / launches
-    hits_per_launch = tot["shaded_hits"] / launches
     fp32_peak = SM_COUNT * FP32_LANES_PER_SM * SM_MAX_GHZ / 1e3  # 37.2 Tflop/s: non-FMA FP32 instruction rate
-    kernels = {
-        "intersect": {
-            "ms": ms["intersect_ms"],
-            "flop": FLOP_PER_RAY_CORNELL * rays_per_launch,
-            # 32 B ray read + 8 B hit written per ray; 4 B queue entry per hit; 16 B radiance read per miss
-            "bytes": 40.0 * rays_per_launch + 4.0 * hits_per_launch + 16.0 * (rays_per_launch - hits_per_launch),
-        },
-        "shade": {
-            "ms": ms["shade_ms"],
-            "flop": (FLOP_PER_SURVIVING_BOUNCE * surviving + FLOP_PER_KILLED_HIT * killed) / launches,
-            # per hit: 4 B queue + 64 B state + 8 B hit read; per survivor 64 B written
-            "bytes": 76.0 * hits_per_launch + 64.0 * surviving / launches,
-        },
-    }
-    name = max(kernels, key=lambda k: kernels[k]["ms"])
-    k = kernels[name]
-    dur = k["ms"] * 1e-3
-    achieved = k["flop"] / dur / 1e12 if dur > 0 else 0.0
-    hbm_achieved = k["bytes"] / dur / 1e9 if dur > 0 else 0.0
+    extra = {}
+    if persistent:
+        launches = max(1, tot["kernel_launches"])
+        name = "k_persistent"
+        ms = sum(s["gpu_ms"] for s in stats_list) / launches
+        flop = (FLOP_PER_RAY_CORNELL * tot["rays"] + FLOP_PER_SURVIVING_BOUNCE * surviving +
+                FLOP_PER_KILLED_HIT * killed) / launches
+        # path state never leaves the registers: the only algorithmic traffic is the framebuffer read-modify-write
+        # (16 B read + 16 B written) of paths that end with non-zero radiance
+        nbytes = 32.0 * tot["contributions"] / launches
+        extra["rays_per_launch"] = tot["rays"] / launches
+    else:
+        launches = max(1, tot["iterations"])
+        stage = {k: statistics.mean(s[k] for s in stats_list)
+                 for k in ("intersect_ms", "shade_ms", "raygen_ms", "accumulate_ms")}
+        rays_per_launch = tot["rays"] / launches
+        hits_per_launch = tot["shaded_hits"] / launches
+        kernels = {
+            "intersect": {
+                "ms": stage["intersect_ms"], "flop": FLOP_PER_RAY_CORNELL * rays_per_launch,
+                # 32 B ray read + 8 B hit written per ray; 4 B queue entry per hit; 16 B radiance read per miss
+                "bytes": 40.0 * rays_per_launch + 4.0 * hits_per_launch + 16.0 * (rays_per_launch - hits_per_launch)},
+            "shade": {
+                "ms": stage["shade_ms"],
+                "flop": (FLOP_PER_SURVIVING_BOUNCE * surviving + FLOP_PER_KILLED_HIT * killed) / launches,
+                # per hit: 4 B queue + 64 B state + 8 B hit read; per survivor 64 B written
+                "bytes": 76.0 * hits_per_launch + 64.0 * surviving / launches},
+        }
+        which = max(kernels, key=lambda k: kernels[k]["ms"])
+        name, ms, flop, nbytes = f"k_{which}", kernels[which]["ms"], kernels[which]["flop"], kernels[which]["bytes"]
+        extra["stage_ms_per_launch"] = stage
+        extra["rays_per_launch"] = rays_per_launch
+    dur = ms * 1e-3
+    achieved = flop / dur / 1e12 if dur > 0 else 0.0
+    hbm_achieved = nbytes / dur / 1e9 if dur > 0 else 0.0
     return {
-        "kernel": f"k_{name}", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+        "kernel": name, "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
         "frac": achieved / fp32_peak,
         "peak_source": "148 SM x 128 FP32 lanes x 1.965 GHz, one non-FMA op per lane per clock (SURVEY.md 8d); "
                        "FP32 is not in MEASURED_PEAKS.json",
         "traffic": None,
-        "launch_ms": k["ms"], "flop_per_launch": k["flop"],
+        "launch_ms": ms, "flop_per_launch": flop,
         "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
-                "bytes_per_launch": k["bytes"], "peak_source": hbm_source},
-        "stage_ms_per_launch": ms,
-        "rays_per_launch": rays_per_launch,
+                "bytes_per_launch": nbytes, "peak_source": hbm_source},
+        **extra,
     }
 
 
@@ -265,6 +282,10 @@ def ours(args, flat):
     W, H = args.width, args.height
     npix = W * H
     first, count, total_spp = sample_range(rank, world, args.spp, args.scaling)
+    pipeline = {"default": binding.PIPELINE_DEFAULT, "wavefront": binding.PIPELINE_WAVEFRONT,
+                "persistent": binding.PIPELINE_PERSISTENT}[args.pipeline]
+    persistent = args.pipeline == "persistent" or (args.pipeline == "default" and
+                                                   os.environ.get("CORNELIS_PIPELINE", "") != "wavefront")
     stream = torch.cuda.Stream()
     scene = binding.Scene(flat, device=local_rank)
     scene.set_stream(stream.cuda_stream)
@@ -283,7 +304,7 @@ def ours(args, flat):
         """Inputs resident in HBM, result left in HBM."""
         with torch.cuda.stream(stream):
             st = scene.render_accumulate(W, H, total_spp, first_sample=first, sample_count=count, pool_paths=args.pool,
-                                         stage_timing=True)
+                                         stage_timing=True, pipeline=pipeline)
             reduce_framebuffer(scene)
             stream.synchronize()
             scene.resolve_device(total_spp)
@@ -297,7 +318,8 @@ def ours(args, flat):
         with torch.cuda.stream(stream):
             sc = binding.Scene(flat, device=local_rank)
             sc.set_stream(stream.cuda_stream)
-            sc.render_accumulate(W, H, total_spp, first_sample=first, sample_count=count, pool_paths=args.pool)
+            sc.render_accumulate(W, H, total_spp, first_sample=first, sample_count=count, pool_paths=args.pool,
+                                 pipeline=pipeline)
             reduce_framebuffer(sc)
             stream.synchronize()
             if rank == 0:
@@ -362,7 +384,8 @@ def ours(args, flat):
                 "ms_per_step": 1e3 * e2e_wall_s / args.steps,
                 "path": "cornelis_cuda_scene_create + render_accumulate + (NCCL sum) + resolve into pinned host memory"},
         "gpu_launches": int(timed_launches),
-        "roofline": roofline(collected, hbm_peak, hbm_source, npix),
+        "roofline": roofline(collected, hbm_peak, hbm_source, persistent),
+        "pipeline": "persistent" if persistent else "wavefront",
         "clocks": clocks.summary(),
         "max_depth": max(s["max_depth"] for s in collected),
     }

@@ -57,7 +57,8 @@ class RenderParams(C.Structure):
 
 class RenderStats(C.Structure):
     _fields_ = [("pixel_samples", C.c_uint64), ("rays", C.c_uint64), ("shaded_hits", C.c_uint64),
-                ("iterations", C.c_uint64), ("kernel_launches", C.c_uint64), ("max_depth", C.c_uint32),
+                ("iterations", C.c_uint64), ("kernel_launches", C.c_uint64), ("contributions", C.c_uint64),
+                ("max_depth", C.c_uint32),
                 ("reserved", C.c_uint32), ("gpu_ms", C.c_float), ("intersect_ms", C.c_float),
                 ("shade_ms", C.c_float), ("raygen_ms", C.c_float), ("accumulate_ms", C.c_float)]
 

@@ -501,6 +501,7 @@ int cornelis_cuda_render_accumulate(cornelis_cuda_scene *s, const cornelis_rende
         stats->shaded_hits = c.shaded;
         stats->iterations = c.iterations;
         stats->kernel_launches = launches;
+        stats->contributions = c.contributions;
         stats->max_depth = c.maxDepth;
         cudaEventElapsedTime(&stats->gpu_ms, s->evStart, s->evStop);
         if (profiled) {

@@ -85,6 +85,7 @@ struct Control {
     unsigned long long rays;       // rays intersected
     unsigned long long shaded;     // hits shaded
     unsigned long long iterations; // passes
+    unsigned long long contributions; // finished paths added to the framebuffer
 };
 
 struct RenderConfig {

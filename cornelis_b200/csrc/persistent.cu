@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
     unsigned long long stashNext = 0, stashEnd = 0;
     uint32_t stashPix = 0, stashSmp = 0; // (pixel, local sample) of stashNext
     // statistics
-    uint32_t rays = 0, shaded = 0, started = 0, deepest = 0;
+    uint32_t rays = 0, shaded = 0, started = 0, deepest = 0, contributed = 0;
 
     for (;;) {
         // ---- regeneration: lanes without a path claim camera paths (generateCameraRays, Render.cpp:85-100) ----
@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
             alive = false;
             bool const nonZero = rad.r != 0.0f || rad.g != 0.0f || rad.b != 0.0f;
             bool const finite = isfinite(rad.r) && isfinite(rad.g) && isfinite(rad.b);
+            contributed += nonZero ? 1u : 0u;
             if (nonZero && (finite || !dropNonFinite)) {
                 atomicAdd(&accum[pixel], make_float4(rad.r, rad.g, rad.b, 1.0f));
                 if (accum2)
@@ -155,11 +156,13 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
     rays = __reduce_add_sync(kFull, rays);
     shaded = __reduce_add_sync(kFull, shaded);
     started = __reduce_add_sync(kFull, started);
+    contributed = __reduce_add_sync(kFull, contributed);
     deepest = __reduce_max_sync(kFull, deepest);
     if (lane == 0) {
         atomicAdd(&ctl->rays, static_cast<unsigned long long>(rays));
         atomicAdd(&ctl->shaded, static_cast<unsigned long long>(shaded));
         atomicAdd(&ctl->cursor, static_cast<unsigned long long>(started)); // camera paths actually started
+        atomicAdd(&ctl->contributions, static_cast<unsigned long long>(contributed));
         atomicMax(&ctl->maxDepth, deepest);
     }
 }

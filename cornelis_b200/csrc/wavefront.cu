@@ -174,11 +174,13 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_SHADE_MIN_BLOCKS) k_sh
 // Per-pixel accumulation (Render.cpp:245-248): every finished path adds its radiance to its pixel's running sum
 // with one 128-bit vector reduction (red.global.add.v4.f32); .w counts contributing paths.  With the variance
 // option the squares go to a second float4 image.
-__global__ void __launch_bounds__(kBlockThreads) k_accumulate(const Control *ctl,
+__global__ void __launch_bounds__(kBlockThreads) k_accumulate(Control *ctl,
                                                               const FinishedPath *__restrict__ finished,
                                                               float4 *__restrict__ accum, float4 *__restrict__ accum2,
                                                               bool dropNonFinite) {
     uint32_t const n = ctl->nFinished;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&ctl->contributions, static_cast<unsigned long long>(n));
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
         FinishedPath const f = finished[q];
         if (dropNonFinite && !(isfinite(f.r) && isfinite(f.g) && isfinite(f.b)))
@@ -452,7 +454,7 @@ void launchShade(cudaStream_t s, const LaunchShape &shape, Control *ctl, const R
                                                                              finished);
 }
 
-void launchAccumulate(cudaStream_t s, const LaunchShape &shape, const Control *ctl, const FinishedPath *finished,
+void launchAccumulate(cudaStream_t s, const LaunchShape &shape, Control *ctl, const FinishedPath *finished,
                       float4 *accum, float4 *accum2, bool dropNonFinite) {
     k_accumulate<<<shape.gridAccumulate, kBlockThreads, 0, s>>>(ctl, finished, accum, accum2, dropNonFinite);
 }

@@ -35,7 +35,7 @@ void launchIntersect(cudaStream_t s, const LaunchShape &shape, Control *ctl, con
 void launchShade(cudaStream_t s, const LaunchShape &shape, Control *ctl, const RenderConfig &cfg,
                  const SceneView &scene, const PathPool &in, const PathPool &out, const HitRecord *hits,
                  const uint32_t *hitQueue, FinishedPath *finished);
-void launchAccumulate(cudaStream_t s, const LaunchShape &shape, const Control *ctl, const FinishedPath *finished,
+void launchAccumulate(cudaStream_t s, const LaunchShape &shape, Control *ctl, const FinishedPath *finished,
                       float4 *accum, float4 *accum2, bool dropNonFinite);
 void launchResolve(cudaStream_t s, const LaunchShape &shape, uint32_t npixels, uint32_t samples, const float4 *accum,
                    const float4 *accum2, float *rgb, float *variance);

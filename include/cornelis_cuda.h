@@ -105,6 +105,7 @@ typedef struct cornelis_render_stats {
     uint64_t shaded_hits;   /* hits that reached accumulateAndBounce */
     uint64_t iterations;    /* wavefront passes */
     uint64_t kernel_launches;
+    uint64_t contributions; /* finished paths whose (non-zero) radiance was added to a pixel */
     uint32_t max_depth;     /* deepest path, in bounces */
     uint32_t reserved;
     float gpu_ms;           /* device time of the render, CUDA events on the scene's stream */

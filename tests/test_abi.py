@@ -44,7 +44,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(binding.CameraDesc) == 32 and C.sizeof(binding.MaterialDesc) == 44
     assert C.sizeof(binding.SphereDesc) == 20 and C.sizeof(binding.PlaneDesc) == 40
     assert C.sizeof(binding.RenderParams) == 48
-    assert C.sizeof(binding.RenderStats) == 72
+    assert C.sizeof(binding.RenderStats) == 80
 
 
 def test_no_device_fails_loudly():

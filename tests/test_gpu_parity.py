@@ -355,7 +355,7 @@ def test_sample_sharding_and_determinism(binding):
     assert np.allclose(whole, small_pool, rtol=1e-5, atol=1e-6)
     st_p = sc.render_accumulate(W, H, 64, pipeline=2)
     assert np.allclose(whole, sc.resolve(64), rtol=1e-5, atol=1e-6)
-    for key in ("pixel_samples", "rays", "shaded_hits", "max_depth"):
+    for key in ("pixel_samples", "rays", "shaded_hits", "max_depth", "contributions"):
         assert st_w[key] == st_p[key], key
     other_seed, _ = sc.render(W, H, 64, seed=12345)
     assert not np.allclose(whole, other_seed, rtol=1e-3, atol=1e-4)
