@@ -313,18 +313,31 @@ def ours(args, flat):
             collect.append(st)
         return st
 
+    debug = os.environ.get("CORNELIS_BENCH_DEBUG")
+
     def step_e2e():
         """Through the public call with HOST buffers: scene description up, framebuffer down, every step."""
+        marks = [time.perf_counter()]
         with torch.cuda.stream(stream):
             sc = binding.Scene(flat, device=local_rank)
             sc.set_stream(stream.cuda_stream)
+            marks.append(time.perf_counter())
             sc.render_accumulate(W, H, total_spp, first_sample=first, sample_count=count, pool_paths=args.pool,
                                  pipeline=pipeline)
+            marks.append(time.perf_counter())
             reduce_framebuffer(sc)
             stream.synchronize()
+            torch.cuda.synchronize()
+            marks.append(time.perf_counter())
             if rank == 0:
                 sc.resolve(total_spp, out=pinned_np)
+            marks.append(time.perf_counter())
             sc.close()
+            marks.append(time.perf_counter())
+        if debug:
+            names = ["create", "render", "reduce", "resolve+d2h", "destroy"]
+            print(f"[rank {rank}] e2e " + "  ".join(f"{n} {1e3 * (b - a):.1f} ms" for n, a, b in
+                                                   zip(names, marks, marks[1:])), file=sys.stderr, flush=True)
         return sc.scene_bytes
 
     def sync_all():

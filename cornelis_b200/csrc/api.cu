@@ -108,7 +108,8 @@ struct cornelis_cuda_scene {
     DeviceBuffer<Control> control;
     DeviceBuffer<unsigned long long> claimCursor; // persistent pipeline: next camera path to claim
     int gridPersistent = 0;
-    Control *hostControl = nullptr; // pinned
+    Control hostControlStorage{};
+    Control *hostControl = &hostControlStorage; // 104 bytes: pageable is fine
     DeviceBuffer<float4> accum, accum2;
     bool haveVariance = false;
     DeviceBuffer<float> outRgb, outVar;
@@ -138,8 +139,6 @@ struct cornelis_cuda_scene {
         for (auto &b : stage4)
             b.release();
         stageHits.release();
-        if (hostControl)
-            cudaFreeHost(hostControl);
         if (evStart)
             cudaEventDestroy(evStart);
         if (evStop)
@@ -170,8 +169,6 @@ int ensureFrame(cornelis_cuda_scene *s, uint32_t width, uint32_t height, uint32_
     }
     CB_CUDA(s->control.reserve(1));
     CB_CUDA(s->claimCursor.reserve(1));
-    if (!s->hostControl)
-        CB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&s->hostControl), sizeof(Control)));
     bool const resized = s->width != width || s->height != height;
     if (resized) {
         s->accum.release();
@@ -252,9 +249,10 @@ int cornelis_cuda_scene_create(int device, const cornelis_camera_desc *camera, c
     CB_CUDA(cudaEventCreate(&s->evStop));
     for (auto &e : s->evStage)
         CB_CUDA(cudaEventCreate(&e));
-    cudaDeviceProp prop{};
-    CB_CUDA(cudaGetDeviceProperties(&prop, device));
-    s->shape.numSMs = prop.multiProcessorCount;
+    int numSMs = 0, smemOptin = 0;
+    CB_CUDA(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, device));
+    CB_CUDA(cudaDeviceGetAttribute(&smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    s->shape.numSMs = numSMs;
 
     // SphereData / PlaneData / materials (Scene.cpp:5-53) flattened to the device tables.
     std::vector<DevSphere> hs(n_spheres);
@@ -317,7 +315,7 @@ int cornelis_cuda_scene_create(int device, const cornelis_camera_desc *camera, c
 
     size_t const smem = sizeof(DevSphere) * n_spheres + sizeof(DevPlane) * n_planes + sizeof(DevMaterial) * n_materials +
                         sizeof(uint32_t) * n_spheres;
-    if (smem > static_cast<size_t>(prop.sharedMemPerBlockOptin) - 1024)
+    if (smem > static_cast<size_t>(smemOptin) - 1024)
         return fail(CORNELIS_ERR_INVALID_ARGUMENT,
                     "scene tables exceed the shared-memory staging limit of this build (" + std::to_string(smem) +
                         " bytes)");

@@ -391,3 +391,23 @@ def test_depth_cap_and_argument_errors(binding):
     with pytest.raises(binding.CornelisError) as e:
         sc.render_accumulate(256, 256, 64, pool_paths=65536, progress=lambda done, total: calls.append(done) or 1)
     assert e.value.code == binding.ERR_ABORTED and len(calls) == 1
+
+
+def test_multi_gpu_sample_sharding_single_process(binding):
+    """Two GPUs, one process: each renders half of the sample indices, GPU 0 sums its peer's accumulators over NVLink
+    peer access (cornelis_cuda_reduce_framebuffers); the result equals the one-GPU render of all samples."""
+    if binding.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    flat = scenes.cornell_box()
+    W = H = 128
+    spp = 64
+    one = binding.Scene(flat, device=0)
+    one.render_accumulate(W, H, spp)
+    expect = one.resolve(spp).copy()
+    parts = [binding.Scene(flat, device=d) for d in (0, 1)]
+    for rank, sc in enumerate(parts):
+        sc.render_accumulate(W, H, spp, first_sample=rank * spp // 2, sample_count=spp // 2, variance=True)
+    binding.reduce_framebuffers(parts)
+    got, var = parts[0].resolve(spp, variance=True)
+    assert np.allclose(got, expect, rtol=1e-5, atol=1e-6)
+    assert np.isfinite(var).all() and var.max() > 0
