@@ -16,7 +16,8 @@ LIB_PATH = Path(__file__).resolve().parent / "lib" / "libcornelis_cuda.so"
 # every symbol include/cornelis_cuda.h declares
 EXPORTS = [
     "cornelis_cuda_abi_version", "cornelis_cuda_last_error", "cornelis_cuda_device_count",
-    "cornelis_cuda_scene_create", "cornelis_cuda_scene_destroy", "cornelis_cuda_scene_set_stream", "cornelis_cuda_render_accumulate",
+    "cornelis_cuda_scene_create", "cornelis_cuda_scene_destroy", "cornelis_cuda_scene_set_stream",
+    "cornelis_cuda_scene_set_acceleration", "cornelis_cuda_scene_acceleration", "cornelis_cuda_render_accumulate",
     "cornelis_cuda_framebuffer_device", "cornelis_cuda_reduce_framebuffers", "cornelis_cuda_resolve", "cornelis_cuda_resolve_device",
     "cornelis_cuda_resolve_srgb8",
     "cornelis_cuda_render", "cornelis_cuda_pixel_rays", "cornelis_cuda_intersect",
@@ -92,6 +93,9 @@ def lib():
         L.cornelis_cuda_scene_create.argtypes = [C.c_int, C.POINTER(CameraDesc), vp, sz, vp, sz, vp, sz, C.POINTER(vp)]
         L.cornelis_cuda_scene_destroy.argtypes = [vp]
         L.cornelis_cuda_scene_set_stream.argtypes = [vp, vp]
+        L.cornelis_cuda_scene_set_acceleration.argtypes = [vp, C.c_int]
+        L.cornelis_cuda_scene_acceleration.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_uint32 * 3),
+                                                       C.POINTER(C.c_uint64)]
         L.cornelis_cuda_render_accumulate.argtypes = [vp, C.POINTER(RenderParams), vp, vp, C.POINTER(RenderStats)]
         L.cornelis_cuda_framebuffer_device.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
         L.cornelis_cuda_resolve.argtypes = [vp, i32, vp, vp]
@@ -141,40 +145,44 @@ def _f32(a, shape=None):
 DEFAULT_MATERIAL = [0.5, 0.5, 0.5, 0, 0, 0, 0.2, 0, 0, 0, 1.5]
 
 
+def descriptors(flat):
+    """The C-ABI description structs of a flat scene (cornelis_b200.scenes): camera, sphere, plane and material arrays
+    (scene material 0, the default material, prepended) plus the numpy views they were filled from."""
+    cam = CameraDesc()
+    c = _f32(flat["camera"], (8,))
+    cam.origin[:] = c[0:3]
+    cam.look_at[:] = c[3:6]
+    cam.aspect, cam.horizontal_fov = float(c[6]), float(c[7])
+    sph = _f32(flat["spheres"], (-1, 4))
+    smat = np.asarray(flat["sphere_mat"], np.int32)
+    pl = _f32(flat["planes"], (-1, 9))
+    pmat = np.asarray(flat["plane_mat"], np.int32)
+    mats = np.concatenate([np.asarray([DEFAULT_MATERIAL], np.float32), _f32(flat["materials"], (-1, 11))])
+    S = (SphereDesc * max(len(sph), 1))()
+    if len(sph):
+        rec = np.zeros(len(sph), dtype=[("c", np.float32, 3), ("r", np.float32), ("m", np.int32)])
+        rec["c"], rec["r"], rec["m"] = sph[:, 0:3], sph[:, 3], smat
+        C.memmove(S, rec.ctypes.data, rec.nbytes)
+    P = (PlaneDesc * max(len(pl), 1))()
+    if len(pl):
+        rec = np.zeros(len(pl), dtype=[("n", np.float32, 3), ("p", np.float32, 3), ("e", np.float32, 3), ("m", np.int32)])
+        rec["n"], rec["p"], rec["e"], rec["m"] = pl[:, 0:3], pl[:, 3:6], pl[:, 6:9], pmat
+        C.memmove(P, rec.ctypes.data, rec.nbytes)
+    M = (MaterialDesc * len(mats))()
+    C.memmove(M, np.ascontiguousarray(mats, np.float32).ctypes.data, mats.nbytes)
+    return cam, S, P, M, (sph, pl, mats)
+
+
+ACCEL_AUTO, ACCEL_NONE, ACCEL_GRID = 0, 1, 2
+
+
 class Scene:
     """A scene resident on one GPU: SceneData (reference Scene.cpp:40-53) uploaded behind the C-ABI."""
 
     def __init__(self, flat, device: int = 0):
         self.handle = None
         L = lib()
-        cam = CameraDesc()
-        c = _f32(flat["camera"], (8,))
-        cam.origin[:] = c[0:3]
-        cam.look_at[:] = c[3:6]
-        cam.aspect, cam.horizontal_fov = float(c[6]), float(c[7])
-        sph = _f32(flat["spheres"], (-1, 4))
-        smat = np.asarray(flat["sphere_mat"], np.int32)
-        pl = _f32(flat["planes"], (-1, 9))
-        pmat = np.asarray(flat["plane_mat"], np.int32)
-        mats = np.concatenate([np.asarray([DEFAULT_MATERIAL], np.float32), _f32(flat["materials"], (-1, 11))])
-        S = (SphereDesc * max(len(sph), 1))()
-        for i, (row, m) in enumerate(zip(sph, smat)):
-            S[i].center[:] = row[0:3]
-            S[i].radius = float(row[3])
-            S[i].material = int(m)
-        P = (PlaneDesc * max(len(pl), 1))()
-        for i, (row, m) in enumerate(zip(pl, pmat)):
-            P[i].normal[:] = row[0:3]
-            P[i].point[:] = row[3:6]
-            P[i].extents[:] = row[6:9]
-            P[i].material = int(m)
-        M = (MaterialDesc * len(mats))()
-        for i, row in enumerate(mats):
-            M[i].albedo[:] = row[0:3]
-            M[i].emissive[:] = row[3:6]
-            M[i].roughness = float(row[6])
-            M[i].reflection_tint[:] = row[7:10]
-            M[i].ior = float(row[10])
+        cam, S, P, M, (sph, pl, mats) = descriptors(flat)
         self.n_spheres, self.n_planes, self.n_materials = len(sph), len(pl), len(mats)
         self.scene_bytes = C.sizeof(cam) + C.sizeof(SphereDesc) * len(sph) + C.sizeof(PlaneDesc) * len(pl) + \
             C.sizeof(MaterialDesc) * len(mats)
@@ -200,6 +208,15 @@ class Scene:
         _check(lib().cornelis_cuda_scene_set_stream(self.handle, C.c_void_p(cuda_stream) if cuda_stream else None))
 
     # ---- hot path --------------------------------------------------------------------------------------------------
+    def set_acceleration(self, mode: int):
+        """ACCEL_AUTO / ACCEL_NONE (exhaustive scan from shared memory) / ACCEL_GRID (uniform grid over the spheres)."""
+        _check(lib().cornelis_cuda_scene_set_acceleration(self.handle, int(mode)))
+
+    def acceleration(self):
+        on, dims, refs = C.c_int(0), (C.c_uint32 * 3)(), C.c_uint64(0)
+        _check(lib().cornelis_cuda_scene_acceleration(self.handle, C.byref(on), C.byref(dims), C.byref(refs)))
+        return dict(grid=bool(on.value), dims=tuple(dims), references=refs.value)
+
     def _params(self, width, height, samples, first_sample=0, sample_count=0, max_depth=0, seed=DEFAULT_SEED,
                 variance=False, keep=False, stage_timing=False, drop_nonfinite=False, pipeline=PIPELINE_DEFAULT,
                 pool_paths=0):

@@ -14,6 +14,7 @@
 #include "device_types.h"
 #include "materials.cuh"
 #include "math.cuh"
+#include "scene_tables.h"
 #include "wavefront.h"
 
 using namespace cornelis_b200;
@@ -86,6 +87,8 @@ DevCamera makeCamera(const cornelis_camera_desc &c) {
     return cam;
 }
 
+constexpr size_t kAutoGridSpheres = 128; // CORNELIS_ACCEL_AUTO: scenes with at least this many spheres use the grid
+
 } // namespace
 
 struct cornelis_cuda_scene {
@@ -99,6 +102,15 @@ struct cornelis_cuda_scene {
     DeviceBuffer<DevPlane> planes;
     DeviceBuffer<DevMaterial> materials;
     SceneView view{};
+    // acceleration structure (built on first use)
+    std::vector<cornelis_sphere_desc> hostSpheres;
+    double boxMin[3] = {0, 0, 0}, boxMax[3] = {0, 0, 0}; // spheres, plane rectangles and the camera eye
+    int accelMode = CORNELIS_ACCEL_AUTO;
+    bool gridBuilt = false, gridUsable = false;
+    DevGrid grid{};
+    uint64_t gridItems = 0;
+    DeviceBuffer<uint32_t> gridCellStart, gridCellItems;
+    int smemOptin = 0;
     // wavefront state
     uint32_t width = 0, height = 0;
     DeviceBuffer<float4> pool[2][4];
@@ -127,6 +139,7 @@ struct cornelis_cuda_scene {
         if (stream)
             cudaStreamSynchronize(stream);
         spheres.release(), sphereMaterial.release(), planes.release(), materials.release();
+        gridCellStart.release(), gridCellItems.release();
         for (auto &half : pool)
             for (auto &b : half)
                 b.release();
@@ -187,6 +200,55 @@ int checkScene(cornelis_cuda_scene *s) {
     if (!s)
         return fail(CORNELIS_ERR_INVALID_ARGUMENT, "scene handle is null");
     CB_CUDA(cudaSetDevice(s->device));
+    return CORNELIS_OK;
+}
+
+// Chooses between the exhaustive scan (all tables staged in shared memory) and the uniform grid (spheres stay in
+// global memory), builds and uploads the grid on first use, and re-derives the launch shapes.
+int applyAcceleration(cornelis_cuda_scene *s, int mode) {
+    size_t const nS = s->view.nSpheres, nP = s->view.nPlanes, nM = s->view.nMaterials;
+    auto tableBytes = [&](bool spheresInShared) {
+        size_t const k = spheresInShared ? nS : 0;
+        return sizeof(DevSphere) * k + sizeof(DevPlane) * nP + sizeof(DevMaterial) * nM + sizeof(uint32_t) * k;
+    };
+    size_t const limit = static_cast<size_t>(s->smemOptin) - 1024;
+    bool wantGrid = nS > 0 && (mode == CORNELIS_ACCEL_GRID || (mode == CORNELIS_ACCEL_AUTO && nS >= kAutoGridSpheres));
+    if (mode == CORNELIS_ACCEL_AUTO && !wantGrid && nS > 0 && tableBytes(true) > limit)
+        wantGrid = true;
+    if (wantGrid && !s->gridBuilt) {
+        HostGrid h;
+        s->gridUsable = buildGrid(s->hostSpheres.data(), s->hostSpheres.size(), s->boxMin, s->boxMax, h);
+        s->gridBuilt = true;
+        if (s->gridUsable) {
+            CB_CUDA(s->gridCellStart.reserve(h.cellStart.size()));
+            CB_CUDA(s->gridCellItems.reserve(h.cellItems.size()));
+            CB_CUDA(cudaMemcpyAsync(s->gridCellStart.ptr, h.cellStart.data(), h.cellStart.size() * sizeof(uint32_t),
+                                    cudaMemcpyHostToDevice, s->stream));
+            CB_CUDA(cudaMemcpyAsync(s->gridCellItems.ptr, h.cellItems.data(), h.cellItems.size() * sizeof(uint32_t),
+                                    cudaMemcpyHostToDevice, s->stream));
+            CB_CUDA(cudaStreamSynchronize(s->stream));
+            s->grid = h.g;
+            s->grid.cellStart = s->gridCellStart.ptr;
+            s->grid.cellItems = s->gridCellItems.ptr;
+            s->gridItems = h.cellStart.back();
+        }
+    }
+    if (wantGrid && !s->gridUsable) {
+        if (mode == CORNELIS_ACCEL_GRID)
+            return fail(CORNELIS_ERR_INVALID_ARGUMENT, "the grid cannot be built for this scene (degenerate or non-finite bounds)");
+        wantGrid = false;
+    }
+    size_t const smem = tableBytes(!wantGrid);
+    if (smem > limit)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT,
+                    "scene tables exceed the shared-memory staging limit of this build (" + std::to_string(smem) +
+                        " bytes)");
+    DevGrid off{};
+    s->view.grid = wantGrid ? s->grid : off;
+    s->accelMode = mode;
+    s->shape.sceneSmemBytes = smem;
+    CB_CUDA(configureKernels(s->shape));
+    CB_CUDA(configurePersistent(s->shape, wantGrid, s->gridPersistent));
     return CORNELIS_OK;
 }
 
@@ -264,26 +326,7 @@ int cornelis_cuda_scene_create(int device, const cornelis_camera_desc *camera, c
     }
     std::vector<DevPlane> hp(n_planes);
     for (size_t i = 0; i < n_planes; i++) {
-        const cornelis_plane_desc &d = planes[i];
-        Basis const b = constructBasis(V3{d.normal[0], d.normal[1], d.normal[2]}); // Geometry.cpp:165, hoisted
-        DevPlane p{};
-        p.px = d.point[0], p.py = d.point[1], p.pz = d.point[2], p.width = d.extents[0];
-        p.nx = d.normal[0], p.ny = d.normal[1], p.nz = d.normal[2], p.height = d.extents[1];
-        p.tx = b.T.x, p.ty = b.T.y, p.tz = b.T.z;
-        p.material = d.material >= 0 ? static_cast<uint32_t>(d.material) : 0u;
-        p.bx = b.B.x, p.by = b.B.y, p.bz = b.B.z;
-        // Axis class for the exact fast path of closestHit: the normal is +-e_k and constructBasis produced the
-        // in-plane axes closestHit assumes (x: T=z, B=y; y: T=x, B=z; z: T=x, B=y), all with unit magnitude.
-        auto unitAxis = [](float x, float y, float z) -> int {
-            if (fabsf(x) == 1.0f && y == 0.0f && z == 0.0f) return 0;
-            if (x == 0.0f && fabsf(y) == 1.0f && z == 0.0f) return 1;
-            if (x == 0.0f && y == 0.0f && fabsf(z) == 1.0f) return 2;
-            return 3;
-        };
-        int const kN = unitAxis(p.nx, p.ny, p.nz), kT = unitAxis(p.tx, p.ty, p.tz), kB = unitAxis(p.bx, p.by, p.bz);
-        bool const expected = (kN == 0 && kT == 2 && kB == 1) || (kN == 1 && kT == 0 && kB == 2) ||
-                              (kN == 2 && kT == 0 && kB == 1);
-        p.pad = expected ? static_cast<uint32_t>(kN) : 3u;
+        DevPlane const p = makeDevPlane(planes[i]);
         hp[i] = p;
     }
     std::vector<DevMaterial> hm(n_materials);
@@ -313,15 +356,12 @@ int cornelis_cuda_scene_create(int device, const cornelis_camera_desc *camera, c
     s->view.nMaterials = static_cast<uint32_t>(n_materials);
     s->view.camera = makeCamera(*camera);
 
-    size_t const smem = sizeof(DevSphere) * n_spheres + sizeof(DevPlane) * n_planes + sizeof(DevMaterial) * n_materials +
-                        sizeof(uint32_t) * n_spheres;
-    if (smem > static_cast<size_t>(smemOptin) - 1024)
-        return fail(CORNELIS_ERR_INVALID_ARGUMENT,
-                    "scene tables exceed the shared-memory staging limit of this build (" + std::to_string(smem) +
-                        " bytes)");
-    s->shape.sceneSmemBytes = smem;
-    CB_CUDA(configureKernels(s->shape));
-    CB_CUDA(configurePersistent(s->shape, s->gridPersistent));
+    // bounding box of every possible ray origin (sizes the grid's error bounds)
+    s->hostSpheres.assign(spheres, spheres + n_spheres);
+    sceneOriginBox(*camera, spheres, n_spheres, hp.data(), n_planes, s->boxMin, s->boxMax);
+    s->smemOptin = smemOptin;
+    if (int rc = applyAcceleration(s, CORNELIS_ACCEL_AUTO))
+        return rc;
 
     guard.p = nullptr;
     *out_scene = s;
@@ -338,6 +378,28 @@ int cornelis_cuda_scene_set_stream(cornelis_cuda_scene *s, void *cudaStream) {
         return rc;
     CB_CUDA(cudaStreamSynchronize(s->stream));
     s->stream = cudaStream ? static_cast<cudaStream_t>(cudaStream) : s->ownStream;
+    return CORNELIS_OK;
+}
+
+int cornelis_cuda_scene_set_acceleration(cornelis_cuda_scene *s, int mode) {
+    if (int rc = checkScene(s))
+        return rc;
+    if (mode != CORNELIS_ACCEL_AUTO && mode != CORNELIS_ACCEL_NONE && mode != CORNELIS_ACCEL_GRID)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "unknown acceleration mode");
+    CB_CUDA(cudaStreamSynchronize(s->stream));
+    return applyAcceleration(s, mode);
+}
+
+int cornelis_cuda_scene_acceleration(cornelis_cuda_scene *s, int *grid_enabled, uint32_t dims[3], uint64_t *references) {
+    if (int rc = checkScene(s))
+        return rc;
+    bool const on = s->view.grid.enabled != 0;
+    if (grid_enabled)
+        *grid_enabled = on ? 1 : 0;
+    if (dims)
+        dims[0] = on ? s->grid.nx : 0, dims[1] = on ? s->grid.ny : 0, dims[2] = on ? s->grid.nz : 0;
+    if (references)
+        *references = on ? s->gridItems : 0;
     return CORNELIS_OK;
 }
 

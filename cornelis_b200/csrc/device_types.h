@@ -38,6 +38,24 @@ struct DevCamera {   // PerspectiveCamera (Camera.hpp:57-60), produced by lookAt
     float vx, vy, vz, pad3;
 };
 
+// Uniform grid over the spheres.  Every sphere is listed, by ascending index, in every cell
+// its padded bounding box overlaps; closestHitGrid walks the cells a ray crosses front to back and runs the SAME
+// per-sphere test on the listed spheres, so hit ids and t are those of the exhaustive scan (see geometry.cuh for the
+// argument and api.cu buildGrid for the padding).
+struct DevGrid {
+    float minx, miny, minz;        // lower corner of the grid
+    float maxx, maxy, maxz;        // upper corner
+    float cellx, celly, cellz;     // cell edge lengths
+    float invx, invy, invz;        // their reciprocals
+    float rminx, rminy, rminz;     // "trusted region": ray origins inside it are covered by the error bound the
+    float rmaxx, rmaxy, rmaxz;     //   padding was derived from; other rays take the exhaustive scan
+    float margin;                  // slack (a distance) on the front-to-back termination test
+    uint32_t nx, ny, nz;           // resolution
+    uint32_t enabled;              // 0: scan all spheres from shared memory
+    const uint32_t *cellStart;     // nx*ny*nz + 1 offsets into cellItems
+    const uint32_t *cellItems;     // sphere indices, ascending within a cell
+};
+
 struct SceneView {
     const DevSphere *spheres;
     const uint32_t *sphereMaterial;
@@ -45,6 +63,7 @@ struct SceneView {
     const DevMaterial *materials;
     uint32_t nSpheres, nPlanes, nMaterials, pad;
     DevCamera camera;
+    DevGrid grid;
 };
 
 // Path pool: four float4 arrays — 64 B per path.

@@ -36,15 +36,19 @@ struct SharedScene {
     const uint32_t *sphereMaterial;
 };
 
-__host__ __device__ inline size_t sharedSceneBytes(uint32_t nSpheres, uint32_t nPlanes, uint32_t nMaterials) {
-    return sizeof(DevSphere) * nSpheres + sizeof(DevPlane) * nPlanes + sizeof(DevMaterial) * nMaterials +
-           sizeof(uint32_t) * nSpheres;
+// With the grid enabled the spheres (and their material ids) stay in global memory — a ray touches a few dozen of
+// them through the read-only cache — and only planes and materials are staged.
+__host__ __device__ inline size_t sharedSceneBytes(uint32_t nSpheres, uint32_t nPlanes, uint32_t nMaterials,
+                                                   bool spheresInShared) {
+    size_t const s = spheresInShared ? nSpheres : 0u;
+    return sizeof(DevSphere) * s + sizeof(DevPlane) * nPlanes + sizeof(DevMaterial) * nMaterials + sizeof(uint32_t) * s;
 }
 
 // Cooperative 16-byte copies global -> shared; every table is a multiple of 16 bytes except the id list.
 __device__ __forceinline__ SharedScene stageScene(const SceneView &scene, unsigned char *smem, bool wantMaterials) {
     float4 *dst = reinterpret_cast<float4 *>(smem);
-    uint32_t const nS4 = scene.nSpheres;                          // 1 float4 per sphere
+    bool const spheresInShared = scene.grid.enabled == 0u;
+    uint32_t const nS4 = spheresInShared ? scene.nSpheres : 0u;   // 1 float4 per sphere
     uint32_t const nP4 = scene.nPlanes * 4;                       // 4 float4 per plane
     uint32_t const nM4 = wantMaterials ? scene.nMaterials * 4 : 0; // 4 float4 per material
     const float4 *srcS = reinterpret_cast<const float4 *>(scene.spheres);
@@ -57,16 +61,27 @@ __device__ __forceinline__ SharedScene stageScene(const SceneView &scene, unsign
     for (uint32_t k = threadIdx.x; k < nM4; k += blockDim.x)
         dst[nS4 + nP4 + k] = srcM[k];
     uint32_t *ids = reinterpret_cast<uint32_t *>(dst + nS4 + nP4 + scene.nMaterials * 4);
-    if (wantMaterials)
+    if (wantMaterials && spheresInShared)
         for (uint32_t k = threadIdx.x; k < scene.nSpheres; k += blockDim.x)
             ids[k] = scene.sphereMaterial[k];
     __syncthreads();
     SharedScene s;
-    s.spheres = reinterpret_cast<const DevSphere *>(dst);
+    s.spheres = spheresInShared ? reinterpret_cast<const DevSphere *>(dst) : scene.spheres;
     s.planes = reinterpret_cast<const DevPlane *>(dst + nS4);
     s.materials = reinterpret_cast<const DevMaterial *>(dst + nS4 + nP4);
-    s.sphereMaterial = ids;
+    s.sphereMaterial = spheresInShared ? ids : scene.sphereMaterial;
     return s;
+}
+
+// The intersect stage for either scene representation.  kGrid is a template parameter of the kernels (the host picks
+// the instantiation from SceneView::grid.enabled) so the few-primitive kernels keep their register budget.
+template <bool kGrid>
+__device__ __forceinline__ void closestHitScene(bool live, V3 o, V3 d, const SharedScene &sh, const SceneView &scene,
+                                                float &tBest, int32_t &primBest) {
+    if (kGrid)
+        closestHitGrid(live, o, d, scene, sh.planes, tBest, primBest);
+    else
+        closestHit(live, o, d, sh.spheres, scene.nSpheres, sh.planes, scene.nPlanes, tBest, primBest);
 }
 
 // ------------------------------------------------------------------------------------------------ compaction --

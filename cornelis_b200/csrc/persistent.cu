@@ -29,6 +29,7 @@ constexpr unsigned long long kClaim = 1024; // camera paths a warp claims per at
 #define CORNELIS_PERSISTENT_MIN_BLOCKS 4
 #endif
 
+template <bool kGrid>
 __global__ void __launch_bounds__(kBlockThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
     k_persistent(RenderConfig cfg, SceneView scene, unsigned long long *__restrict__ cursor, unsigned long long limit,
                  float4 *__restrict__ accum, float4 *__restrict__ accum2, bool dropNonFinite, Control *__restrict__ ctl) {
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
         // ---- intersect (Render.cpp:110-150) ----
         float t = INFINITY; // IntersectionData::reset, Geometry.cpp:7-12
         int32_t prim = -1;
-        closestHit(alive, org, dir, sh.spheres, scene.nSpheres, sh.planes, scene.nPlanes, t, prim);
+        closestHitScene<kGrid>(alive, org, dir, sh, scene, t, prim);
 
         // ---- accumulateAndBounce (Render.cpp:167-218) ----
         bool finished = false;
@@ -167,15 +168,16 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
     }
 }
 
-cudaError_t configurePersistent(LaunchShape &shape, int &grid) {
+template <bool kGrid>
+static cudaError_t configureOne(const LaunchShape &shape, int &grid) {
     cudaError_t e;
     if (shape.sceneSmemBytes > 48 * 1024)
-        if ((e = cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if ((e = cudaFuncSetAttribute(k_persistent<kGrid>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(shape.sceneSmemBytes))) != cudaSuccess)
             return e;
     int blocks = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_persistent, kBlockThreads, shape.sceneSmemBytes)) !=
-        cudaSuccess)
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_persistent<kGrid>, kBlockThreads,
+                                                           shape.sceneSmemBytes)) != cudaSuccess)
         return e;
     if (const char *env = std::getenv("CORNELIS_PERSISTENT_BLOCKS_PER_SM"))
         if (std::atoi(env) > 0)
@@ -184,11 +186,19 @@ cudaError_t configurePersistent(LaunchShape &shape, int &grid) {
     return cudaSuccess;
 }
 
+cudaError_t configurePersistent(LaunchShape &shape, bool gridScene, int &grid) {
+    return gridScene ? configureOne<true>(shape, grid) : configureOne<false>(shape, grid);
+}
+
 void launchPersistent(cudaStream_t s, const LaunchShape &shape, int grid, const RenderConfig &cfg, const SceneView &scene,
                       unsigned long long *cursor, unsigned long long limit, float4 *accum, float4 *accum2,
                       bool dropNonFinite, Control *ctl) {
-    k_persistent<<<grid, kBlockThreads, shape.sceneSmemBytes, s>>>(cfg, scene, cursor, limit, accum, accum2, dropNonFinite,
-                                                                  ctl);
+    if (scene.grid.enabled)
+        k_persistent<true><<<grid, kBlockThreads, shape.sceneSmemBytes, s>>>(cfg, scene, cursor, limit, accum, accum2,
+                                                                             dropNonFinite, ctl);
+    else
+        k_persistent<false><<<grid, kBlockThreads, shape.sceneSmemBytes, s>>>(cfg, scene, cursor, limit, accum, accum2,
+                                                                              dropNonFinite, ctl);
 }
 
 } // namespace cornelis_b200

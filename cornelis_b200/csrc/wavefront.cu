@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_raygen(const Control *ctl, Re
 #ifndef CORNELIS_INTERSECT_MIN_BLOCKS
 #define CORNELIS_INTERSECT_MIN_BLOCKS 6
 #endif
+template <bool kGrid>
 __global__ void __launch_bounds__(kBlockThreads, CORNELIS_INTERSECT_MIN_BLOCKS) k_intersect(Control *ctl, SceneView scene, PathPool pool,
                                                              HitRecord *__restrict__ hits,
                                                              uint32_t *__restrict__ hitQueue,
@@ -84,8 +85,7 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_INTERSECT_MIN_BLOCKS) 
         }
         float t = INFINITY; // IntersectionData::reset, Geometry.cpp:7-12
         int32_t prim = -1;
-        closestHit(valid, V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, sh.spheres, scene.nSpheres, sh.planes,
-                   scene.nPlanes, t, prim);
+        closestHitScene<kGrid>(valid, V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, sh, scene, t, prim);
         if (valid) {
             hit = t < INFINITY; // Render.cpp:146
             hits[i] = HitRecord{t, prim};
@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_pixel_rays(DevCamera cam, uin
 
 // The intersect stage on a plain float4 ray batch — the same closestHit as k_intersect without the queues.
 // Used by cornelis_cuda_intersect(_device): parity tests and the intersection microbench (config 3).
+template <bool kGrid>
 __global__ void __launch_bounds__(kBlockThreads) k_intersect_batch(SceneView scene, size_t n,
                                                                    const float4 *__restrict__ org,
                                                                    const float4 *__restrict__ dir,
@@ -285,8 +286,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_intersect_batch(SceneView sce
         }
         float t = INFINITY;
         int32_t prim = -1;
-        closestHit(valid, V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, sh.spheres, scene.nSpheres, sh.planes,
-                   scene.nPlanes, t, prim);
+        closestHitScene<kGrid>(valid, V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, sh, scene, t, prim);
         if (valid)
             hits[i] = HitRecord{t, prim};
     }
@@ -443,8 +443,12 @@ void launchRaygen(cudaStream_t s, const LaunchShape &shape, const Control *ctl, 
 
 void launchIntersect(cudaStream_t s, const LaunchShape &shape, Control *ctl, const SceneView &scene,
                      const PathPool &pool, HitRecord *hits, uint32_t *hitQueue, FinishedPath *finished) {
-    k_intersect<<<shape.gridIntersect, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, scene, pool, hits, hitQueue,
-                                                                                 finished);
+    if (scene.grid.enabled)
+        k_intersect<true><<<shape.gridIntersectGrid, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, scene, pool, hits,
+                                                                                               hitQueue, finished);
+    else
+        k_intersect<false><<<shape.gridIntersect, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, scene, pool, hits,
+                                                                                            hitQueue, finished);
 }
 
 void launchShade(cudaStream_t s, const LaunchShape &shape, Control *ctl, const RenderConfig &cfg,
@@ -484,8 +488,12 @@ void launchPixelRays(cudaStream_t s, const LaunchShape &shape, const DevCamera &
 
 void launchIntersectBatch(cudaStream_t s, const LaunchShape &shape, const SceneView &scene, size_t n,
                           const float4 *org, const float4 *dir, HitRecord *hits) {
-    k_intersect_batch<<<gridFor(n, shape.numSMs, shape.blocksPerSM), kBlockThreads, shape.sceneSmemBytes, s>>>(
-        scene, n, org, dir, hits);
+    if (scene.grid.enabled)
+        k_intersect_batch<true><<<gridFor(n, shape.numSMs, shape.blocksPerSM), kBlockThreads, shape.sceneSmemBytes, s>>>(
+            scene, n, org, dir, hits);
+    else
+        k_intersect_batch<false><<<gridFor(n, shape.numSMs, shape.blocksPerSM), kBlockThreads, shape.sceneSmemBytes, s>>>(
+            scene, n, org, dir, hits);
 }
 
 void launchHitSurface(cudaStream_t s, const LaunchShape &shape, const SceneView &scene, size_t n, const float4 *org,
@@ -536,11 +544,15 @@ cudaError_t configureKernels(LaunchShape &shape) {
     int const bytes = static_cast<int>(shape.sceneSmemBytes);
     // Scenes whose tables exceed the default 48 KB of dynamic shared memory opt in to the large carve-out.
     if (shape.sceneSmemBytes > 48 * 1024) {
-        if ((e = cudaFuncSetAttribute(k_intersect, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
+        if ((e = cudaFuncSetAttribute(k_intersect<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
+            return e;
+        if ((e = cudaFuncSetAttribute(k_intersect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
             return e;
         if ((e = cudaFuncSetAttribute(k_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
             return e;
-        if ((e = cudaFuncSetAttribute(k_intersect_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
+        if ((e = cudaFuncSetAttribute(k_intersect_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
+            return e;
+        if ((e = cudaFuncSetAttribute(k_intersect_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
             return e;
         if ((e = cudaFuncSetAttribute(k_hit_surface, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
             return e;
@@ -558,7 +570,9 @@ cudaError_t configureKernels(LaunchShape &shape) {
     };
     if ((e = resident(k_raygen, 0, shape.gridRaygen)) != cudaSuccess)
         return e;
-    if ((e = resident(k_intersect, shape.sceneSmemBytes, shape.gridIntersect)) != cudaSuccess)
+    if ((e = resident(k_intersect<false>, shape.sceneSmemBytes, shape.gridIntersect)) != cudaSuccess)
+        return e;
+    if ((e = resident(k_intersect<true>, shape.sceneSmemBytes, shape.gridIntersectGrid)) != cudaSuccess)
         return e;
     if ((e = resident(k_shade, shape.sceneSmemBytes, shape.gridShade)) != cudaSuccess)
         return e;

@@ -14,7 +14,7 @@ struct LaunchShape {
     int blocksPerSM = 4;      // resident 256-thread CTAs per SM for the stage entry points
     // Persistent grids: numSMs x (CTAs of that kernel resident per SM, from the occupancy calculator), so every CTA
     // is resident for the whole launch and the grid-stride loops split the pool evenly.
-    int gridRaygen = 592, gridIntersect = 592, gridShade = 592, gridAccumulate = 592;
+    int gridRaygen = 592, gridIntersect = 592, gridIntersectGrid = 592, gridShade = 592, gridAccumulate = 592;
     size_t sceneSmemBytes = 0;
 };
 
@@ -22,7 +22,7 @@ struct LaunchShape {
 cudaError_t configureKernels(LaunchShape &shape);
 
 // persistent-thread pipeline (persistent.cu)
-cudaError_t configurePersistent(LaunchShape &shape, int &grid);
+cudaError_t configurePersistent(LaunchShape &shape, bool gridScene, int &grid);
 void launchPersistent(cudaStream_t s, const LaunchShape &shape, int grid, const RenderConfig &cfg, const SceneView &scene,
                       unsigned long long *cursor, unsigned long long limit, float4 *accum, float4 *accum2,
                       bool dropNonFinite, Control *ctl);

@@ -139,6 +139,16 @@ int cornelis_cuda_scene_destroy(cornelis_cuda_scene *scene);
  * scene's own non-blocking stream).  Lets a host framework bracket the work with its own events. */
 int cornelis_cuda_scene_set_stream(cornelis_cuda_scene *scene, void *cuda_stream);
 
+/* How the intersect stage finds the closest sphere.  The reference scans every sphere for every ray
+ * (Render.cpp:115-123); the grid evaluates the same per-sphere test on the spheres registered in the cells a ray
+ * crosses and returns the same hit primitive and t bit for bit (cornelis_b200/csrc/geometry.cuh).
+ * AUTO (the state after scene_create): grid for scenes with many spheres, exhaustive scan from shared memory otherwise. */
+enum { CORNELIS_ACCEL_AUTO = 0, CORNELIS_ACCEL_NONE = 1, CORNELIS_ACCEL_GRID = 2 };
+int cornelis_cuda_scene_set_acceleration(cornelis_cuda_scene *scene, int mode);
+/* What is in use: grid on/off, its resolution, and the number of (cell, sphere) references.  Any output may be NULL. */
+int cornelis_cuda_scene_acceleration(cornelis_cuda_scene *scene, int *grid_enabled, uint32_t dims[3],
+                                     uint64_t *references);
+
 /* ---- the hot path: replaces the tile loop + integrateTile (Render.cpp:220-255, 327-354) ------------------------- */
 
 /* Render the sample range into the device accumulators (sum of per-sample radiance per pixel). */

@@ -411,3 +411,100 @@ def test_multi_gpu_sample_sharding_single_process(binding):
     got, var = parts[0].resolve(spp, variance=True)
     assert np.allclose(got, expect, rtol=1e-5, atol=1e-6)
     assert np.isfinite(var).all() and var.max() > 0
+
+
+# ------------------------------------------------------------------------- uniform grid (BASELINE config 4) --
+
+def test_grid_bit_exact_against_exhaustive_and_oracle(binding, oracle):
+    """10 000 spheres (BASELINE.json configs[3]): the grid returns the exhaustive scan's primitive id and t bit for
+    bit — against the oracle on 2^16 rays, against the exhaustive shared-memory kernel on 2^21 rays of three kinds
+    (camera rays, random rays through the cloud, bounce-like rays 1e-4 off a surface)."""
+    flat = scenes.many_spheres(10000)
+    sc = binding.Scene(flat)
+    assert sc.acceleration()["grid"]                       # AUTO picks the grid for this scene
+    info = sc.acceleration()
+    assert info["references"] < 40 * 10000 and min(info["dims"]) >= 8
+    ref = oracle.scene(flat)
+    rng = np.random.default_rng(21)
+    n = 1 << 16
+    pi, pj = rng.integers(0, 1920, n), rng.integers(0, 1080, n)
+    p1, p2 = rng.random(n, dtype=np.float32), rng.random(n, dtype=np.float32)
+    o1, d1 = sc.pixel_rays(1920, 1080, pi, pj, p1, p2)
+    want = ref.intersect(o1, d1)
+    got = sc.intersect(o1, d1)
+    assert np.array_equal(got["prim"], want["prim"]) and bit_equal(got["t"], want["t"])
+    assert bit_equal(got["P"], want["P"]) and bit_equal(got["N"], want["N"]) and np.array_equal(got["mat"], want["mat"])
+    # bounce-like rays from the oracle's hit points
+    g = unit(rng, n)
+    hit = want["prim"] >= 0
+    o3 = (want["P"][hit] + g[hit] * np.float32(1e-4)).astype(np.float32)
+    d3 = g[hit]
+    want3 = ref.intersect(o3, d3)
+    got3 = sc.intersect(o3, d3, surface=False)
+    assert np.array_equal(got3["prim"], want3["prim"]) and bit_equal(got3["t"], want3["t"])
+    # large batch: grid vs exhaustive kernel
+    m = 1 << 21
+    o2, d2 = scenes.microbench_rays(m, seed=77)
+    o2[: m // 2, 1] = np.abs(o2[: m // 2, 1])
+    pi, pj = rng.integers(0, 1920, m // 4), rng.integers(0, 1080, m // 4)
+    oc, dc = sc.pixel_rays(1920, 1080, pi, pj, rng.random(m // 4, dtype=np.float32), rng.random(m // 4, dtype=np.float32))
+    org, dirs = np.concatenate([o2, oc]), np.concatenate([d2, dc])
+    org[:64] *= np.float32(100.0)                          # outside the trusted region: exhaustive fallback path
+    dirs[64:96, 0] = 0.0
+    dirs[96:100] = np.float32(np.nan)
+    dirs[100:104] = 0.0
+    with_grid = sc.intersect(org, dirs, surface=False)
+    sc.set_acceleration(binding.ACCEL_NONE)
+    assert not sc.acceleration()["grid"]
+    exhaustive = sc.intersect(org, dirs, surface=False)
+    assert np.array_equal(with_grid["prim"], exhaustive["prim"])
+    assert bit_equal(with_grid["t"], exhaustive["t"])
+    assert (exhaustive["prim"] >= 0).mean() > 0.3 and ((exhaustive["prim"] >= 0) & (exhaustive["prim"] < 10000)).mean() > 0.2
+    sc.set_acceleration(binding.ACCEL_AUTO)
+    assert sc.acceleration()["grid"]
+
+
+@pytest.mark.parametrize("pipeline", [p[1] for p in PIPELINES], ids=[p[0] for p in PIPELINES])
+def test_grid_render_traces_the_same_paths(binding, pipeline):
+    """Rendering through the grid and through the exhaustive scan traces identical paths: identical ray, hit, depth
+    and contribution counts; images equal up to fp32 summation order."""
+    flat = scenes.many_spheres(3000, 16)
+    sc = binding.Scene(flat)
+    W, H, spp = 160, 90, 32
+    sc.set_acceleration(binding.ACCEL_NONE)
+    st_a = sc.render_accumulate(W, H, spp, pipeline=pipeline, max_depth=64)
+    img_a = sc.resolve(spp).copy()
+    sc.set_acceleration(binding.ACCEL_GRID)
+    st_b = sc.render_accumulate(W, H, spp, pipeline=pipeline, max_depth=64)
+    img_b = sc.resolve(spp)
+    for key in ("pixel_samples", "rays", "shaded_hits", "max_depth", "contributions"):
+        assert st_a[key] == st_b[key], key
+    finite = np.isfinite(img_a) & np.isfinite(img_b)
+    assert finite.mean() > 0.999 and np.allclose(img_a[finite], img_b[finite], rtol=1e-4, atol=1e-5)
+    # the Cornell box can be forced through the grid as well (4 spheres)
+    box = binding.Scene(scenes.cornell_box())
+    s1 = box.render_accumulate(64, 64, 32, pipeline=pipeline)
+    a = box.resolve(32).copy()
+    box.set_acceleration(binding.ACCEL_GRID)
+    assert box.acceleration()["grid"]
+    s2 = box.render_accumulate(64, 64, 32, pipeline=pipeline)
+    assert s1["rays"] == s2["rays"] and s1["contributions"] == s2["contributions"]
+    assert np.allclose(a, box.resolve(32), rtol=1e-4, atol=1e-5)
+
+
+def test_config4_image_within_three_sigma(binding, oracle):
+    """BASELINE.json configs[3] (10 000 spheres, 64 mixed materials, max depth 64) at a reduced frame: the GPU render
+    through the grid against the oracle's brute-force render, 3-sigma per pixel."""
+    flat = scenes.many_spheres(10000)
+    W, H, spp_ref, spp = 96, 54, 48, 1024
+    ref = oracle.scene(flat).render(W, H, spp_ref, tile=(32, 18), variance=True, stats=True)
+    sc = binding.Scene(flat)
+    st = sc.render_accumulate(W, H, spp, variance=True, max_depth=64)
+    mean, var = sc.resolve(spp, variance=True)
+    ok, diff, sigma = _three_sigma(mean, var, spp, ref["mean"], ref["variance"], spp_ref)
+    good = np.isfinite(mean).all(axis=2)
+    rmse = float(np.sqrt(np.mean(diff[good] ** 2)))
+    print(f"config 4: 3-sigma fraction {ok.mean():.5f}  RMSE {rmse:.5f}  rays/sample {st['rays'] / st['pixel_samples']:.3f}"
+          f" (oracle {ref['stats']['rays'] / ref['stats']['pixel_samples']:.3f})")
+    assert ok.mean() >= 0.98, ok.mean()
+    assert abs(st["rays"] / st["pixel_samples"] - ref["stats"]["rays"] / ref["stats"]["pixel_samples"]) < 0.05

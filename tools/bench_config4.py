@@ -1,0 +1,56 @@
+"""Config 4 (BASELINE.json configs[3]): 10 000 random spheres over a 4000x4000 floor, 64 mixed Oren-Nayar / glossy
+materials, 1920x1080 at 1024 spp, max depth 64 — rendered through the uniform grid.  Prints one JSON line with
+pixel-samples/s and rays/s for both pipelines, the exhaustive-scan kernel on a bounded sample beside it, and the
+reference's CPU loop (oracle/_ref when present, else the oracle port) on a bounded sample of the same frame.
+
+    python tools/bench_config4.py [--spp 1024] [--width 1920 --height 1080] [--no-cpu]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from cornelis_b200 import binding, scenes  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--width", type=int, default=1920)
+ap.add_argument("--height", type=int, default=1080)
+ap.add_argument("--spp", type=int, default=1024)
+ap.add_argument("--spheres", type=int, default=10000)
+ap.add_argument("--no-cpu", action="store_true")
+ap.add_argument("--no-exhaustive", action="store_true")
+args = ap.parse_args()
+
+W, H = args.width, args.height
+flat = scenes.many_spheres(args.spheres, aspect=H / W)
+scene = binding.Scene(flat)
+out = {"workload": f"{args.spheres} spheres + floor, 64 materials, {W}x{H}, {args.spp} spp, max depth 64",
+       "acceleration": scene.acceleration()}
+scene.render_accumulate(W, H, 4, max_depth=64)  # warm-up
+for name, pipeline in (("persistent", binding.PIPELINE_PERSISTENT), ("wavefront", binding.PIPELINE_WAVEFRONT)):
+    st = scene.render_accumulate(W, H, args.spp, max_depth=64, pipeline=pipeline)
+    out[name] = {"msamples_per_s": st["pixel_samples"] / st["gpu_ms"] / 1e3, "mrays_per_s": st["rays"] / st["gpu_ms"] / 1e3,
+                 "gpu_ms": st["gpu_ms"], "rays_per_sample": st["rays"] / st["pixel_samples"], "max_depth": st["max_depth"],
+                 "kernel_launches": st["kernel_launches"]}
+if not args.no_exhaustive:
+    # the reference's own strategy on the GPU (every sphere for every ray, tables in shared memory), bounded sample
+    scene.set_acceleration(binding.ACCEL_NONE)
+    spp_small = max(1, args.spp // 256)
+    st = scene.render_accumulate(W, H, spp_small, max_depth=64)
+    out["exhaustive_scan"] = {"msamples_per_s": st["pixel_samples"] / st["gpu_ms"] / 1e3,
+                              "mrays_per_s": st["rays"] / st["gpu_ms"] / 1e3, "sample": f"{spp_small} spp"}
+    scene.set_acceleration(binding.ACCEL_AUTO)
+if not args.no_cpu:
+    from oracle import loader
+    ora = loader.best()
+    w, h = W // 10, H // 10
+    t0 = time.time()
+    r = ora.scene(scenes.many_spheres(args.spheres, aspect=h / w)).render(w, h, 8, tile=(w // 4 or 1, h // 4 or 1), stats=True)
+    dt = time.time() - t0
+    out["cpu_baseline"] = {"msamples_per_s": r["stats"]["pixel_samples"] / dt / 1e6, "mrays_per_s": r["stats"]["rays"] / dt / 1e6,
+                           "kind": "reference" if ora.kind == "reference" else "port", "cores": os.cpu_count(),
+                           "sample": f"{w}x{h} at 8 spp, {dt:.1f} s"}
+print(json.dumps(out))
