@@ -487,7 +487,10 @@ int cornelis_cuda_render_accumulate(cornelis_cuda_scene *s, const cornelis_rende
     if (persistent) {
         // One launch renders a slice of the camera-path range; between slices the host reports progress and may abort.
         bool const drop = (p->flags & CORNELIS_RENDER_DROP_NONFINITE) != 0;
-        uint64_t const slice = std::max<uint64_t>(total / 32 + 1, 1ull << 22);
+        // With a callback the render is cut into at least two slices so that it is consulted at least once.
+        uint64_t slice = std::max<uint64_t>(total / 32 + 1, 1ull << 22);
+        if (progress && total > 1)
+            slice = std::min<uint64_t>(slice, (total + 1) / 2);
         uint64_t done = 0;
         while (done < total) {
             uint64_t const limit = std::min(total, done + slice);

@@ -173,9 +173,22 @@ __device__ __forceinline__ bool shadeBounce(const DevMaterial &mat, V3 P, V3 N, 
     dir = wIn;                                                              // Render.cpp:208
     float const c = fabsf(dot(wIn, N));
     float const denom = pdf * prob;
-    thr.r *= (f.r * c) / denom;                                             // Render.cpp:210-213, Color.cpp:11-17
-    thr.g *= (f.g * c) / denom;
-    thr.b *= (f.b * c) / denom;
+    // thr *= f * c / denom, Render.cpp:210-213 with RGB / float as three true divisions (Color.cpp:11-17).  One
+    // reciprocal seed serves the three quotients, and zero numerators (black albedo: the light, gold's diffuse part)
+    // stay on the fast path — same bits as the operator (exact_arith.cuh).
+    float const nr = f.r * c, ng = f.g * c, nb = f.b * c;
+    bool const fast = inFastDivisorRange(denom) && (nr == 0.0f || inFastDivideRange(nr)) &&
+                      (ng == 0.0f || inFastDivideRange(ng)) && (nb == 0.0f || inFastDivideRange(nb));
+    if (fast) {
+        float const rD = rcpSeedRefined(denom);
+        thr.r *= divideExactFast0(nr, denom, rD);
+        thr.g *= divideExactFast0(ng, denom, rD);
+        thr.b *= divideExactFast0(nb, denom, rD);
+    } else {
+        thr.r *= nr / denom;
+        thr.g *= ng / denom;
+        thr.b *= nb / denom;
+    }
     return true;
 }
 

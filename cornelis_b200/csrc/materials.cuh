@@ -17,6 +17,7 @@
 #pragma once
 
 #include "device_types.h"
+#include "exact_arith.cuh"
 #include "math.cuh"
 
 namespace cornelis_b200 {
@@ -171,7 +172,8 @@ __device__ __forceinline__ RGBf layeredSample(const DevMaterial &m, V3 wo, float
         float const A = 1.0f - x1;
         float const B = 1.0f + (m.alpha2 - 1.0f) * x1;
         axial = sqrtf(A / B);
-        radial = sqrtf(1.0f - axial * axial);
+        radial = sqrtExact(1.0f - axial * axial); // == sqrtf; near-mirror lobes (gold: alpha^2 = 1e-8) give sqrt(0) here
+                                                  // every time, which sqrtf answers through an out-of-line call
     }
     float const angle = 2.0f * kPi * (diffuse ? x1 : x0); // == float(2.0 * Pi * x): the 48-bit product is exact in double
     double sn, cs;

@@ -34,7 +34,11 @@ inline DevPlane makeDevPlane(const cornelis_plane_desc &d) {
     int const kN = unitAxis(p.nx, p.ny, p.nz), kT = unitAxis(p.tx, p.ty, p.tz), kB = unitAxis(p.bx, p.by, p.bz);
     bool const expected = (kN == 0 && kT == 2 && kB == 1) || (kN == 1 && kT == 0 && kB == 2) ||
                           (kN == 2 && kT == 0 && kB == 1);
-    p.pad = expected ? static_cast<uint32_t>(kN) : 3u;
+    // (the fast path also wants p0's components to be 0 or >= 2^-56: geometry.cuh differenceSafe)
+    auto safe = [](float x) { return !(fabsf(x) < 0x1.0p-56f) || x == 0.0f; };
+    bool const finite = std::isfinite(p.px) && std::isfinite(p.py) && std::isfinite(p.pz) &&
+                        fabsf(p.px) <= 0x1.0p30f && fabsf(p.py) <= 0x1.0p30f && fabsf(p.pz) <= 0x1.0p30f;
+    p.pad = expected && finite && safe(p.px) && safe(p.py) && safe(p.pz) ? static_cast<uint32_t>(kN) : 3u;
     return p;
 }
 

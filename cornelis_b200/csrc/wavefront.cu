@@ -397,12 +397,26 @@ __global__ void __launch_bounds__(kBlockThreads) k_selftest_arith(int mode, unsi
             return __uint_as_float((bits & 0x80000000u) | (static_cast<uint32_t>(e + 127) << 23) | mant);
         };
         if (mode == 0) {
-            float const a = craft(r.v[0], r.v[2], -80, 79), b = craft(r.v[1], r.v[2] >> 3, -40, 39);
-            float const fast = divideExactFast(a, b, rcpSeedRefined(b));
-            bad += __float_as_uint(fast) != __float_as_uint(a / b);
+            float a = craft(r.v[0], r.v[2], -80, 79);
+            float const b = craft(r.v[1], r.v[2] >> 3, -40, 39);
+            float const rb = rcpSeedRefined(b);
+            bad += __float_as_uint(divideExactFast(a, b, rb)) != __float_as_uint(a / b);
+            if ((r.v[3] & 15u) == 0u)
+                a = __uint_as_float(r.v[3] & 0x80000000u); // +-0: the zero-numerator variant must keep the sign
+            bad += __float_as_uint(divideExactFast0(a, b, rb)) != __float_as_uint(a / b);
+            // the per-lane wrapper, with operands inside and outside the fast ranges
+            float const a2 = craft(r.v[0], r.v[2], -126, 126), b2 = craft(r.v[1], r.v[2] >> 3, -126, 126);
+            bad += __float_as_uint(divideExact(a2, b2)) != __float_as_uint(a2 / b2);
+            bad += __float_as_uint(divideExact(a, b2)) != __float_as_uint(a / b2);
         } else {
             float const x = fabsf(craft(r.v[0], r.v[2], -100, 125));
             bad += __float_as_uint(sqrtExactFast(x)) != __float_as_uint(sqrtf(x));
+            float y = fabsf(craft(r.v[1], r.v[2] >> 3, -126, 127));
+            if ((r.v[3] & 15u) == 0u)
+                y = __uint_as_float(r.v[3] & 0x80000000u); // +-0
+            if ((r.v[3] & 15u) == 1u)
+                y = __uint_as_float(r.v[3] >> 9);          // denormals
+            bad += __float_as_uint(sqrtExact(y)) != __float_as_uint(sqrtf(y));
         }
     }
     if (bad)

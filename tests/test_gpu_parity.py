@@ -167,6 +167,31 @@ def test_general_planes_and_odd_rays(binding, oracle):
     assert (a["prim"] >= 9).any() and (a["prim"] == 3).any()
 
 
+def test_rays_starting_on_planes_keep_the_sign_of_zero(binding, oracle):
+    """A bounce off a plane starts ON it about one time in four (o_k == p0_k after rounding): t against that plane is
+    a signed zero whose sign the reference derives from -(diff . N) / (d . N).  The fast path must return the same
+    bits — t = -0.0 included — for normals of either sign and every sign pattern of the other components."""
+    flat = scenes.cornell_box()
+    sc, osc = binding.Scene(flat), oracle.scene(flat)
+    rng = np.random.default_rng(5)
+    n = 120000
+    o = (rng.random((n, 3), dtype=np.float32) * 550 - np.float32([275, 0, 275])).astype(np.float32)
+    d = unit(rng, n)
+    k = np.arange(n) % 6
+    o[k == 0, 0] = np.float32(-275.0)   # left wall   N = +x
+    o[k == 1, 0] = np.float32(275.0)    # right wall  N = -x
+    o[k == 2, 1] = np.float32(555.0)    # roof        N = -y
+    o[k == 3, 1] = np.float32(0.0)      # floor       N = +y   (+0 and, below, -0 origins)
+    o[k == 4, 2] = np.float32(275.0)    # back wall   N = -z
+    o[(np.arange(n) % 12) == 9, 1] = np.float32(-0.0)
+    o[(np.arange(n) % 24) == 5] = np.float32([0, 555, 0])   # the roof's own point, exactly
+    a, b = sc.intersect(o, d, surface=False), osc.intersect(o, d)
+    assert np.array_equal(a["prim"], b["prim"])
+    assert bit_equal(a["t"], b["t"])
+    zero = b["t"] == 0
+    assert zero.sum() > n // 4 and np.signbit(b["t"][zero]).any() and (~np.signbit(b["t"][zero])).any()
+
+
 # ---------------------------------------------------------------------------------------------------- materials --
 
 def _bsdf_inputs(rng, n, n_mat):
@@ -492,19 +517,23 @@ def test_grid_render_traces_the_same_paths(binding, pipeline):
     assert np.allclose(a, box.resolve(32), rtol=1e-4, atol=1e-5)
 
 
-def test_config4_image_within_three_sigma(binding, oracle):
+def test_config4_image_within_three_sigma(binding, golden):
     """BASELINE.json configs[3] (10 000 spheres, 64 mixed materials, max depth 64) at a reduced frame: the GPU render
-    through the grid against the oracle's brute-force render, 3-sigma per pixel."""
+    through the grid against the reference's brute-force render (tests/golden/make_golden.py config4: 48x27 at
+    2048 spp), 3-sigma per pixel.  The estimator is heavy-tailed here — 2 % of the materials are lights — so both
+    sides need thousands of samples per pixel for their variance estimates to mean anything."""
+    g = golden("render_config4_48x27_2048spp.npz")
     flat = scenes.many_spheres(10000)
-    W, H, spp_ref, spp = 96, 54, 48, 1024
-    ref = oracle.scene(flat).render(W, H, spp_ref, tile=(32, 18), variance=True, stats=True)
+    W, H, spp_ref, spp = 48, 27, int(g["spp"]), 4096
     sc = binding.Scene(flat)
     st = sc.render_accumulate(W, H, spp, variance=True, max_depth=64)
     mean, var = sc.resolve(spp, variance=True)
-    ok, diff, sigma = _three_sigma(mean, var, spp, ref["mean"], ref["variance"], spp_ref)
+    ok, diff, sigma = _three_sigma(mean, var, spp, g["mean"], g["variance"], spp_ref)
     good = np.isfinite(mean).all(axis=2)
     rmse = float(np.sqrt(np.mean(diff[good] ** 2)))
+    rays_ref = float(g["rays"]) / (W * H * spp_ref)
     print(f"config 4: 3-sigma fraction {ok.mean():.5f}  RMSE {rmse:.5f}  rays/sample {st['rays'] / st['pixel_samples']:.3f}"
-          f" (oracle {ref['stats']['rays'] / ref['stats']['pixel_samples']:.3f})")
-    assert ok.mean() >= 0.98, ok.mean()
-    assert abs(st["rays"] / st["pixel_samples"] - ref["stats"]["rays"] / ref["stats"]["pixel_samples"]) < 0.05
+          f" (reference {rays_ref:.3f})")
+    assert ok.mean() >= 0.99, ok.mean()
+    assert abs(mean[good].mean() / g["mean"][good].mean() - 1.0) < 0.03
+    assert abs(st["rays"] / st["pixel_samples"] - rays_ref) < 0.02
