@@ -11,7 +11,8 @@ from pathlib import Path
 
 import numpy as np
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libcornelis_cuda.so"
+# CORNELIS_CUDA_LIB: an alternative build of the same library (tools/variants.py A/B runs), never a fallback
+LIB_PATH = Path(os.environ.get("CORNELIS_CUDA_LIB") or Path(__file__).resolve().parent / "lib" / "libcornelis_cuda.so")
 
 # every symbol include/cornelis_cuda.h declares
 EXPORTS = [

@@ -101,6 +101,7 @@ struct cornelis_cuda_scene {
     DeviceBuffer<uint32_t> sphereMaterial;
     DeviceBuffer<DevPlane> planes;
     DeviceBuffer<DevMaterial> materials;
+    DeviceBuffer<uint32_t> planeOrder;
     SceneView view{};
     // acceleration structure (built on first use)
     std::vector<cornelis_sphere_desc> hostSpheres;
@@ -139,7 +140,7 @@ struct cornelis_cuda_scene {
         if (stream)
             cudaStreamSynchronize(stream);
         spheres.release(), sphereMaterial.release(), planes.release(), materials.release();
-        gridCellStart.release(), gridCellItems.release();
+        gridCellStart.release(), gridCellItems.release(), planeOrder.release();
         for (auto &half : pool)
             for (auto &b : half)
                 b.release();
@@ -209,7 +210,8 @@ int applyAcceleration(cornelis_cuda_scene *s, int mode) {
     size_t const nS = s->view.nSpheres, nP = s->view.nPlanes, nM = s->view.nMaterials;
     auto tableBytes = [&](bool spheresInShared) {
         size_t const k = spheresInShared ? nS : 0;
-        return sizeof(DevSphere) * k + sizeof(DevPlane) * nP + sizeof(DevMaterial) * nM + sizeof(uint32_t) * k;
+        size_t const order = (sizeof(uint32_t) * nP + 15u) & ~static_cast<size_t>(15u);
+        return sizeof(DevSphere) * k + sizeof(DevPlane) * nP + sizeof(DevMaterial) * nM + order + sizeof(uint32_t) * k;
     };
     size_t const limit = static_cast<size_t>(s->smemOptin) - 1024;
     bool wantGrid = nS > 0 && (mode == CORNELIS_ACCEL_GRID || (mode == CORNELIS_ACCEL_AUTO && nS >= kAutoGridSpheres));
@@ -329,6 +331,18 @@ int cornelis_cuda_scene_create(int device, const cornelis_camera_desc *camera, c
         DevPlane const p = makeDevPlane(planes[i]);
         hp[i] = p;
     }
+    // plane indices by axis class, then index (SceneView::planeOrder)
+    std::vector<uint32_t> order(n_planes ? n_planes : 1, 0u);
+    uint32_t classEnd[4] = {0, 0, 0, 0};
+    {
+        size_t k = 0;
+        for (uint32_t c = 0; c < 4; c++) {
+            for (size_t i = 0; i < n_planes; i++)
+                if (hp[i].pad == c)
+                    order[k++] = static_cast<uint32_t>(i);
+            classEnd[c] = static_cast<uint32_t>(k);
+        }
+    }
     std::vector<DevMaterial> hm(n_materials);
     for (size_t i = 0; i < n_materials; i++)
         hm[i] = makeDevMaterial(materials[i].albedo, materials[i].emissive, materials[i].roughness,
@@ -338,6 +352,8 @@ int cornelis_cuda_scene_create(int device, const cornelis_camera_desc *camera, c
     CB_CUDA(s->sphereMaterial.reserve(n_spheres ? n_spheres : 1));
     CB_CUDA(s->planes.reserve(n_planes ? n_planes : 1));
     CB_CUDA(s->materials.reserve(n_materials));
+    CB_CUDA(s->planeOrder.reserve(order.size()));
+    CB_CUDA(cudaMemcpyAsync(s->planeOrder.ptr, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
     if (n_spheres) {
         CB_CUDA(cudaMemcpyAsync(s->spheres.ptr, hs.data(), n_spheres * sizeof(DevSphere), cudaMemcpyHostToDevice, s->stream));
         CB_CUDA(cudaMemcpyAsync(s->sphereMaterial.ptr, hsm.data(), n_spheres * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
@@ -354,6 +370,8 @@ int cornelis_cuda_scene_create(int device, const cornelis_camera_desc *camera, c
     s->view.nSpheres = static_cast<uint32_t>(n_spheres);
     s->view.nPlanes = static_cast<uint32_t>(n_planes);
     s->view.nMaterials = static_cast<uint32_t>(n_materials);
+    s->view.planeOrder = s->planeOrder.ptr;
+    s->view.planeEnd[0] = classEnd[0], s->view.planeEnd[1] = classEnd[1], s->view.planeEnd[2] = classEnd[2];
     s->view.camera = makeCamera(*camera);
 
     // bounding box of every possible ray origin (sizes the grid's error bounds)
@@ -467,6 +485,8 @@ int cornelis_cuda_render_accumulate(cornelis_cuda_scene *s, const cornelis_rende
     cfg.key1 = static_cast<uint32_t>(p->seed >> 32);
     cfg.dx = 1.0f / static_cast<float>(p->width);  // Render.cpp:31
     cfg.dy = 1.0f / static_cast<float>(p->height);
+    cfg.byWidth = makeFastDiv(cfg.width);
+    cfg.keys = makePhiloxKeys(cfg.key0, cfg.key1);
 
     Control init{};
     init.total = total;
@@ -488,9 +508,13 @@ int cornelis_cuda_render_accumulate(cornelis_cuda_scene *s, const cornelis_rende
         // One launch renders a slice of the camera-path range; between slices the host reports progress and may abort.
         bool const drop = (p->flags & CORNELIS_RENDER_DROP_NONFINITE) != 0;
         // With a callback the render is cut into at least two slices so that it is consulted at least once.
-        uint64_t slice = std::max<uint64_t>(total / 32 + 1, 1ull << 22);
-        if (progress && total > 1)
-            slice = std::min<uint64_t>(slice, (total + 1) / 2);
+        // Without a callback there is nothing to report or abort: one launch, one drain at the end.
+        uint64_t slice = total;
+        if (progress) {
+            slice = std::max<uint64_t>(total / 32 + 1, 1ull << 22);
+            if (total > 1)
+                slice = std::min<uint64_t>(slice, (total + 1) / 2);
+        }
         uint64_t done = 0;
         while (done < total) {
             uint64_t const limit = std::min(total, done + slice);
@@ -925,7 +949,7 @@ int cornelis_cuda_rng_uniforms(cornelis_cuda_scene *s, uint64_t seed, size_t n, 
 int cornelis_cuda_selftest_arith(cornelis_cuda_scene *s, int mode, uint64_t n, uint32_t seed, uint64_t *mismatches) {
     if (int rc = checkScene(s))
         return rc;
-    if (!mismatches || (mode != 0 && mode != 1))
+    if (!mismatches || mode < 0 || mode > 2)
         return fail(CORNELIS_ERR_INVALID_ARGUMENT, "bad argument");
     DeviceBuffer<unsigned long long> counter;
     CB_CUDA(counter.reserve(1));

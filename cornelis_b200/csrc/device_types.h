@@ -8,23 +8,26 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "fastdiv.h"
+#include "rng.cuh"
+
 namespace cornelis_b200 {
 
 // Scene tables.  Built on the host with the reference's own arithmetic (api.cu) and staged into shared memory by
 // every kernel that intersects or shades.
-struct DevSphere {   // float4
+struct __align__(16) DevSphere {   // float4
     float cx, cy, cz; // center (Scene.cpp:12-14)
     float r2;         // sphereRadius * sphereRadius, the only form Geometry.cpp:81 uses
 };
 
-struct DevPlane {    // 4 x float4
+struct __align__(16) DevPlane {    // 4 x float4
     float px, py, pz, width;   // point on the plane; extents[0] (Scene.cpp:28-33)
     float nx, ny, nz, height;  // normal;             extents[1]
     float tx, ty, tz; uint32_t material; // constructBasis(normal).T (Math.hpp:424-434), hoisted out of Geometry.cpp:165
     float bx, by, bz; uint32_t pad;      // constructBasis(normal).B; pad = axis class: 0/1/2 normal = +-x/y/z, 3 general
 };
 
-struct DevMaterial { // 4 x float4 — StandardMaterial (Materials.hpp:325-338) with its constants folded
+struct __align__(16) DevMaterial { // 4 x float4 — StandardMaterial (Materials.hpp:325-338) with its constants folded
     float er, eg, eb, on_a;        // emission; OrenNayarBRDF::a_ (Materials.hpp:208)
     float dr, dg, db, on_b;        // albedo / Pi (Materials.hpp:226, Color.cpp:11-17); OrenNayarBRDF::b_
     float tr, tg, tb, alpha;       // glossy tint; GlossyBRDF::alpha_ = roughness^2 (Materials.hpp:296-299)
@@ -62,8 +65,24 @@ struct SceneView {
     const DevPlane *planes;
     const DevMaterial *materials;
     uint32_t nSpheres, nPlanes, nMaterials, pad;
+    // Plane indices sorted by axis class (then by index): [0, planeEnd[0]) have normals along x, [planeEnd[0],
+    // planeEnd[1]) along y, [planeEnd[1], planeEnd[2]) along z, the rest are general.  closestHit runs one tight loop
+    // per class instead of dispatching on the class of every plane.
+    const uint32_t *planeOrder;
+    uint32_t planeEnd[3];
+    uint32_t pad2;
     DevCamera camera;
     DevGrid grid;
+};
+
+// Scene tables staged in dynamic shared memory: [spheres][planes][materials][plane order][sphere material ids]
+// (kernels.cuh stageScene).  With the grid the sphere tables stay in global memory and the pointers say so.
+struct SharedScene {
+    const DevSphere *spheres;
+    const DevPlane *planes;
+    const DevMaterial *materials;
+    const uint32_t *planeOrder;
+    const uint32_t *sphereMaterial;
 };
 
 // Path pool: four float4 arrays — 64 B per path.
@@ -116,6 +135,8 @@ struct RenderConfig {
     uint32_t pad;
     uint32_t key0, key1; // Philox key = seed
     float dx, dy;       // 1.0f / width, 1.0f / height (Render.cpp:31)
+    FastDiv byWidth;    // pixel -> row without a software divide
+    PhiloxKeys keys;    // the ten Philox round keys of (key0, key1)
 };
 
 } // namespace cornelis_b200

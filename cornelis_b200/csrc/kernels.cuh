@@ -28,29 +28,26 @@ constexpr int kWarpsPerBlock = kBlockThreads / 32;
 
 // --------------------------------------------------------------------------------------------- shared scene --
 
-// Scene tables staged in dynamic shared memory: [spheres][planes][materials][sphere material ids].
-struct SharedScene {
-    const DevSphere *spheres;
-    const DevPlane *planes;
-    const DevMaterial *materials;
-    const uint32_t *sphereMaterial;
-};
-
 // With the grid enabled the spheres (and their material ids) stay in global memory — a ray touches a few dozen of
-// them through the read-only cache — and only planes and materials are staged.
+// them through the read-only cache — and only planes, materials and the plane order are staged.
 __host__ __device__ inline size_t sharedSceneBytes(uint32_t nSpheres, uint32_t nPlanes, uint32_t nMaterials,
                                                    bool spheresInShared) {
     size_t const s = spheresInShared ? nSpheres : 0u;
-    return sizeof(DevSphere) * s + sizeof(DevPlane) * nPlanes + sizeof(DevMaterial) * nMaterials + sizeof(uint32_t) * s;
+    size_t const order = (sizeof(uint32_t) * nPlanes + 15u) & ~static_cast<size_t>(15u);
+    return sizeof(DevSphere) * s + sizeof(DevPlane) * nPlanes + sizeof(DevMaterial) * nMaterials + order +
+           sizeof(uint32_t) * s;
 }
 
-// Cooperative 16-byte copies global -> shared; every table is a multiple of 16 bytes except the id list.
+// Cooperative 16-byte copies global -> shared; every table is a multiple of 16 bytes except the two index lists.
+// kGrid is a compile-time parameter so that, without the grid, every pointer provably addresses shared memory
+// (LDS.128 instead of generic loads).
+template <bool kGrid>
 __device__ __forceinline__ SharedScene stageScene(const SceneView &scene, unsigned char *smem, bool wantMaterials) {
     float4 *dst = reinterpret_cast<float4 *>(smem);
-    bool const spheresInShared = scene.grid.enabled == 0u;
-    uint32_t const nS4 = spheresInShared ? scene.nSpheres : 0u;   // 1 float4 per sphere
+    uint32_t const nS4 = kGrid ? 0u : scene.nSpheres;             // 1 float4 per sphere
     uint32_t const nP4 = scene.nPlanes * 4;                       // 4 float4 per plane
-    uint32_t const nM4 = wantMaterials ? scene.nMaterials * 4 : 0; // 4 float4 per material
+    uint32_t const nM4 = scene.nMaterials * 4;                    // 4 float4 per material
+    uint32_t const nO4 = (scene.nPlanes + 3u) / 4u;               // plane order, padded to 16 bytes
     const float4 *srcS = reinterpret_cast<const float4 *>(scene.spheres);
     const float4 *srcP = reinterpret_cast<const float4 *>(scene.planes);
     const float4 *srcM = reinterpret_cast<const float4 *>(scene.materials);
@@ -58,18 +55,23 @@ __device__ __forceinline__ SharedScene stageScene(const SceneView &scene, unsign
         dst[k] = srcS[k];
     for (uint32_t k = threadIdx.x; k < nP4; k += blockDim.x)
         dst[nS4 + k] = srcP[k];
-    for (uint32_t k = threadIdx.x; k < nM4; k += blockDim.x)
-        dst[nS4 + nP4 + k] = srcM[k];
-    uint32_t *ids = reinterpret_cast<uint32_t *>(dst + nS4 + nP4 + scene.nMaterials * 4);
-    if (wantMaterials && spheresInShared)
+    if (wantMaterials)
+        for (uint32_t k = threadIdx.x; k < nM4; k += blockDim.x)
+            dst[nS4 + nP4 + k] = srcM[k];
+    uint32_t *order = reinterpret_cast<uint32_t *>(dst + nS4 + nP4 + nM4);
+    for (uint32_t k = threadIdx.x; k < scene.nPlanes; k += blockDim.x)
+        order[k] = scene.planeOrder[k];
+    uint32_t *ids = reinterpret_cast<uint32_t *>(dst + nS4 + nP4 + nM4 + nO4);
+    if (wantMaterials && !kGrid)
         for (uint32_t k = threadIdx.x; k < scene.nSpheres; k += blockDim.x)
             ids[k] = scene.sphereMaterial[k];
     __syncthreads();
     SharedScene s;
-    s.spheres = spheresInShared ? reinterpret_cast<const DevSphere *>(dst) : scene.spheres;
+    s.spheres = kGrid ? scene.spheres : reinterpret_cast<const DevSphere *>(dst);
     s.planes = reinterpret_cast<const DevPlane *>(dst + nS4);
     s.materials = reinterpret_cast<const DevMaterial *>(dst + nS4 + nP4);
-    s.sphereMaterial = spheresInShared ? ids : scene.sphereMaterial;
+    s.planeOrder = order;
+    s.sphereMaterial = kGrid ? scene.sphereMaterial : ids;
     return s;
 }
 
@@ -81,7 +83,7 @@ __device__ __forceinline__ void closestHitScene(bool live, V3 o, V3 d, const Sha
     if (kGrid)
         closestHitGrid(live, o, d, scene, sh.planes, tBest, primBest);
     else
-        closestHit(live, o, d, sh.spheres, scene.nSpheres, sh.planes, scene.nPlanes, tBest, primBest);
+        closestHit(live, o, d, sh, scene, tBest, primBest);
 }
 
 // ------------------------------------------------------------------------------------------------ compaction --
@@ -141,7 +143,15 @@ CB_HD V3 cameraDirection(const DevCamera &c, float x, float y) {
     V3 xu{x * c.ux, x * c.uy, x * c.uz};
     V3 yv{y * c.vx, y * c.vy, y * c.vz};
     V3 d = (V3{c.cx, c.cy, c.cz} + xu) + yv;
-    float s = 1.0f / sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+    float const len2 = d.x * d.x + d.y * d.y + d.z * d.z;
+    float s;
+#ifdef __CUDA_ARCH__
+    if (inFastNormalizeRange(len2)) {
+        float len;
+        sqrtAndReciprocalExactFast(len2, len, s); // == 1.0f / sqrtf(len2), bit for bit (exact_arith.cuh)
+    } else
+#endif
+        s = 1.0f / sqrtf(len2);
     return V3{d.x * s, d.y * s, d.z * s};
 }
 

@@ -50,7 +50,7 @@ __device__ __forceinline__ float approxRcp(float x) {
     asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ float approxDiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float approxDiv(float a, float b) { return a * approxRcp(b); } // (__fdividef adds range scaling)
 
 // x^5 for Schlick's (1 - cos)^5 (Materials.cpp:41 uses std::pow(x, 5.0f)): exact-ish in double, rounded once.
 CB_HD float pow5(float x) {

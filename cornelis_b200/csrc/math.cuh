@@ -8,7 +8,11 @@
 #include <cmath>
 #include <cuda_runtime.h>
 
+#ifndef CB_HD
 #define CB_HD __host__ __device__ __forceinline__
+#endif
+
+#include "exact_arith.cuh"
 
 namespace cornelis_b200 {
 
@@ -44,12 +48,31 @@ CB_HD V3 cross(V3 a, V3 b) { // Math.hpp:380-384
 
 // Math.hpp:392-398: length below RayEpsilon collapses to the zero vector; otherwise multiply by the ROUNDED
 // reciprocal (not a division per component).
-CB_HD V3 normalize(V3 v) {
-    float len = sqrtf(mag2(v));
+CB_HD V3 normalizeGeneric(V3 v, float x) {
+    float len = sqrtf(x);
     if (isAlmostZero(len))
         return V3{0.0f, 0.0f, 0.0f};
     float s = 1.0f / len;
     return v * V3{s, s, s};
+}
+#ifdef __CUDACC__
+// out of line on the device: lengths outside the fast range are never seen in a render, and six inlined copies of the
+// operator sequences with their slow-path calls cost instruction-cache space in the hot loop
+static __device__ __noinline__ V3 normalizeOutOfRange(V3 v, float x) { return normalizeGeneric(v, x); }
+#endif
+CB_HD V3 normalize(V3 v) {
+    float const x = mag2(v);
+#ifdef __CUDA_ARCH__
+    if (!inFastNormalizeRange(x))
+        return normalizeOutOfRange(v, x);
+    float len, s; // same values as normalizeGeneric, bit for bit (exact_arith.cuh)
+    sqrtAndReciprocalExactFast(x, len, s);
+    if (isAlmostZero(len))
+        return V3{0.0f, 0.0f, 0.0f};
+    return v * V3{s, s, s};
+#else
+    return normalizeGeneric(v, x);
+#endif
 }
 
 struct Basis {

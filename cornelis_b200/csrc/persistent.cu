@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
     k_persistent(RenderConfig cfg, SceneView scene, unsigned long long *__restrict__ cursor, unsigned long long limit,
                  float4 *__restrict__ accum, float4 *__restrict__ accum2, bool dropNonFinite, Control *__restrict__ ctl) {
     extern __shared__ __align__(16) unsigned char smem[];
-    SharedScene const sh = stageScene(scene, smem, true);
+    SharedScene const sh = stageScene<kGrid>(scene, smem, true);
     constexpr unsigned kFull = 0xffffffffu;
     unsigned const lane = threadIdx.x & 31u;
     unsigned const below = (1u << lane) - 1u;
@@ -74,10 +74,14 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
             bool const fromStash = rank < avail;
             unsigned long long const index = fromStash ? stashNext + rank : fresh + (rank - avail);
             // path p = sampleLocal * npixels + pixel, from the stash's (pixel, sample) position: 32-bit arithmetic
-            uint32_t const linear = fromStash ? stashPix + rank : freshPix + (rank - avail);
-            uint32_t const wraps = linear / cfg.npixels;
-            uint32_t const newPixel = linear - wraps * cfg.npixels;
-            uint32_t const newSample = (fromStash ? stashSmp : freshSmp) + wraps;
+            // (at most 32 past the last pixel of a frame: the wrap loops below run zero or one time unless the frame
+            // has fewer than 32 pixels)
+            uint32_t newPixel = fromStash ? stashPix + rank : freshPix + (rank - avail);
+            uint32_t newSample = fromStash ? stashSmp : freshSmp;
+            while (newPixel >= cfg.npixels) {
+                newPixel -= cfg.npixels;
+                newSample++;
+            }
             if (count > avail) {
                 stashNext = fresh + (count - avail);
                 stashEnd = fresh + kClaim;
@@ -87,10 +91,9 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
                 stashNext += count;
                 stashPix += count;
             }
-            { // keep the stash position normalised
-                uint32_t const w = stashPix / cfg.npixels;
-                stashPix -= w * cfg.npixels;
-                stashSmp += w;
+            while (stashPix >= cfg.npixels) { // keep the stash position normalised
+                stashPix -= cfg.npixels;
+                stashSmp++;
             }
             if (need) {
                 if (index >= limit) {
@@ -98,8 +101,8 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
                 } else {
                     pixel = newPixel;
                     sample = cfg.firstSample + newSample;
-                    uint32_t const j = pixel / cfg.width, i = pixel - j * cfg.width;
-                    Philox4 const r = philox4x32_10(pixel, sample, 0u, 0u, cfg.key0, cfg.key1);
+                    uint32_t const j = fastDivide(pixel, cfg.byWidth), i = pixel - j * cfg.width;
+                    Philox4 const r = philox4x32_10(pixel, sample, 0u, 0u, cfg.keys);
                     dir = pixelRayDirection(scene.camera, i, j, cfg.dx, cfg.dy, uniformFromBits(r.v[0]),
                                             uniformFromBits(r.v[1]));
                     org = V3{scene.camera.ex, scene.camera.ey, scene.camera.ez};
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
                 V3 P, N;
                 uint32_t material;
                 hitSurface(org, dir, t, prim, sh.spheres, sh.sphereMaterial, scene.nSpheres, sh.planes, P, N, material);
-                Philox4 const r = philox4x32_10(pixel, sample, depth + 1u, 0u, cfg.key0, cfg.key1);
+                Philox4 const r = philox4x32_10(pixel, sample, depth + 1u, 0u, cfg.keys);
                 bool const survives =
                     shadeBounce(sh.materials[material], P, N, depth, uniformFromBits(r.v[0]), uniformFromBits(r.v[1]),
                                 uniformFromBits(r.v[2]), uniformFromBits(r.v[3]), org, dir, thr, rad);

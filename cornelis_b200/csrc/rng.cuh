@@ -39,6 +39,38 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
     return Philox4{{c0, c1, c2, c3}};
 }
 
+// The ten round keys depend only on the seed: the host expands them once per render into the kernel parameters, so
+// the per-round key bumps disappear from the device code (the keys become constant-bank operands of the xors).
+struct PhiloxKeys {
+    uint32_t k[20]; // k[2r] = key0 + r * W0, k[2r + 1] = key1 + r * W1
+};
+
+inline PhiloxKeys makePhiloxKeys(uint32_t key0, uint32_t key1) {
+    PhiloxKeys keys{};
+    for (uint32_t r = 0; r < 10; r++) {
+        keys.k[2 * r] = key0 + r * 0x9E3779B9u;
+        keys.k[2 * r + 1] = key1 + r * 0xBB67AE85u;
+    }
+    return keys;
+}
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          const PhiloxKeys &keys) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int round = 0; round < 10; round++) {
+        unsigned long long p0 = static_cast<unsigned long long>(M0) * c0;
+        unsigned long long p1 = static_cast<unsigned long long>(M1) * c2;
+        uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ keys.k[2 * round];
+        uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ keys.k[2 * round + 1];
+        c1 = static_cast<uint32_t>(p1);
+        c3 = static_cast<uint32_t>(p0);
+        c0 = n0;
+        c2 = n2;
+    }
+    return Philox4{{c0, c1, c2, c3}};
+}
+
 __host__ __device__ __forceinline__ float uniformFromBits(uint32_t u) {
     return static_cast<float>(u >> 8) * 0x1.0p-24f; // exact: 24-bit integer times a power of two
 }

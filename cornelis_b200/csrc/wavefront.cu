@@ -44,8 +44,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_raygen(const Control *ctl, Re
         uint32_t const wraps = pixel / cfg.npixels;
         pixel -= wraps * cfg.npixels;
         uint32_t const sample = cfg.firstSample + sample0 + wraps;
-        uint32_t const j = pixel / cfg.width, i = pixel - j * cfg.width;
-        Philox4 const r = philox4x32_10(pixel, sample, 0u, 0u, cfg.key0, cfg.key1);
+        uint32_t const j = fastDivide(pixel, cfg.byWidth), i = pixel - j * cfg.width;
+        Philox4 const r = philox4x32_10(pixel, sample, 0u, 0u, cfg.keys);
         float const phi1 = uniformFromBits(r.v[0]), phi2 = uniformFromBits(r.v[1]); // Render.cpp:94-95
         V3 const d = pixelRayDirection(cam, i, j, cfg.dx, cfg.dy, phi1, phi2);
         uint32_t const slot = base + k;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_INTERSECT_MIN_BLOCKS) 
                                                              FinishedPath *__restrict__ finished) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t scratch[2][kWarpsPerBlock + 1];
-    SharedScene const sh = stageScene(scene, smem, false);
+    SharedScene const sh = stageScene<kGrid>(scene, smem, false);
     uint32_t const n = ctl->nIn;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         uint32_t const i = base + threadIdx.x;
@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_INTERSECT_MIN_BLOCKS) 
 #ifndef CORNELIS_SHADE_MIN_BLOCKS
 #define CORNELIS_SHADE_MIN_BLOCKS 5
 #endif
+template <bool kGrid>
 __global__ void __launch_bounds__(kBlockThreads, CORNELIS_SHADE_MIN_BLOCKS) k_shade(Control *ctl, RenderConfig cfg, SceneView scene,
                                                          PathPool in, PathPool out,
                                                          const HitRecord *__restrict__ hits,
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_SHADE_MIN_BLOCKS) k_sh
                                                          FinishedPath *__restrict__ finished) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t scratch[2][kWarpsPerBlock + 1];
-    SharedScene const sh = stageScene(scene, smem, true);
+    SharedScene const sh = stageScene<kGrid>(scene, smem, true);
     uint32_t const n = ctl->nHit;
     uint32_t deepest = 0;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_SHADE_MIN_BLOCKS) k_sh
             V3 P, N;
             uint32_t material;
             hitSurface(org, dir, h.t, h.prim, sh.spheres, sh.sphereMaterial, scene.nSpheres, sh.planes, P, N, material);
-            Philox4 const r = philox4x32_10(pixel, sample, depth + 1u, 0u, cfg.key0, cfg.key1);
+            Philox4 const r = philox4x32_10(pixel, sample, depth + 1u, 0u, cfg.keys);
             alive = shadeBounce(sh.materials[material], P, N, depth, uniformFromBits(r.v[0]), uniformFromBits(r.v[1]),
                                 uniformFromBits(r.v[2]), uniformFromBits(r.v[3]), org, dir, thr, rad);
             depth += 1;
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_intersect_batch(SceneView sce
                                                                    const float4 *__restrict__ dir,
                                                                    HitRecord *__restrict__ hits) {
     extern __shared__ __align__(16) unsigned char smem[];
-    SharedScene const sh = stageScene(scene, smem, false);
+    SharedScene const sh = stageScene<kGrid>(scene, smem, false);
     for (size_t base = static_cast<size_t>(blockIdx.x) * blockDim.x; base < n;
          base += static_cast<size_t>(gridDim.x) * blockDim.x) {
         size_t const i = base + threadIdx.x;
@@ -293,13 +294,14 @@ __global__ void __launch_bounds__(kBlockThreads) k_intersect_batch(SceneView sce
 }
 
 // Expands hit records into the reference's IntersectionData fields (P, N, MaterialId; Geometry.hpp:7-15).
+template <bool kGrid>
 __global__ void __launch_bounds__(kBlockThreads) k_hit_surface(SceneView scene, size_t n,
                                                                const float4 *__restrict__ org,
                                                                const float4 *__restrict__ dir,
                                                                const HitRecord *__restrict__ hits, float *P, float *N,
                                                                int32_t *mat) {
     extern __shared__ __align__(16) unsigned char smem[];
-    SharedScene const sh = stageScene(scene, smem, true);
+    SharedScene const sh = stageScene<kGrid>(scene, smem, true);
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         HitRecord const h = hits[i];
@@ -377,7 +379,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_rng(uint32_t n, uint32_t key0
 
 // Self-test of the exact fast paths of geometry.cuh against the IEEE operators: operands with random sign and
 // mantissa (one in eight with an all-ones / all-zeros / single-bit mantissa) and exponents spanning the ranges the fast
-// paths claim.  mode 0: division, mode 1: square root.  Counts results whose bits differ.
+// paths claim.  mode 0: division, mode 1: square root, mode 2: the normalize pair (sqrt, reciprocal) over EVERY float
+// bit pattern i < 2^32 in its range (n = 2^32 makes it exhaustive).  Counts results whose bits differ.
 __global__ void __launch_bounds__(kBlockThreads) k_selftest_arith(int mode, unsigned long long n, uint32_t seed,
                                                                   unsigned long long *mismatches) {
     unsigned long long bad = 0;
@@ -396,6 +399,17 @@ __global__ void __launch_bounds__(kBlockThreads) k_selftest_arith(int mode, unsi
             int const e = eLo + static_cast<int>((bits >> 23) % static_cast<uint32_t>(eHi - eLo + 1));
             return __uint_as_float((bits & 0x80000000u) | (static_cast<uint32_t>(e + 127) << 23) | mant);
         };
+        if (mode == 2) { // exhaustive: i enumerates float bit patterns; every float in the fast normalize range
+            float const x = __uint_as_float(static_cast<uint32_t>(i));
+            if (i < (1ull << 32) && inFastNormalizeRange(x)) {
+                float len, s;
+                sqrtAndReciprocalExactFast(x, len, s);
+                float const lenRef = sqrtf(x);
+                bad += __float_as_uint(len) != __float_as_uint(lenRef);
+                bad += (__float_as_uint(s) != __float_as_uint(1.0f / lenRef)) ? (1ull << 32) : 0ull; // high word: s
+            }
+            continue;
+        }
         if (mode == 0) {
             float a = craft(r.v[0], r.v[2], -80, 79);
             float const b = craft(r.v[1], r.v[2] >> 3, -40, 39);
@@ -468,8 +482,12 @@ void launchIntersect(cudaStream_t s, const LaunchShape &shape, Control *ctl, con
 void launchShade(cudaStream_t s, const LaunchShape &shape, Control *ctl, const RenderConfig &cfg,
                  const SceneView &scene, const PathPool &in, const PathPool &out, const HitRecord *hits,
                  const uint32_t *hitQueue, FinishedPath *finished) {
-    k_shade<<<shape.gridShade, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, cfg, scene, in, out, hits, hitQueue,
-                                                                             finished);
+    if (scene.grid.enabled)
+        k_shade<true><<<shape.gridShade, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, cfg, scene, in, out, hits,
+                                                                                   hitQueue, finished);
+    else
+        k_shade<false><<<shape.gridShade, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, cfg, scene, in, out, hits,
+                                                                                    hitQueue, finished);
 }
 
 void launchAccumulate(cudaStream_t s, const LaunchShape &shape, Control *ctl, const FinishedPath *finished,
@@ -512,8 +530,12 @@ void launchIntersectBatch(cudaStream_t s, const LaunchShape &shape, const SceneV
 
 void launchHitSurface(cudaStream_t s, const LaunchShape &shape, const SceneView &scene, size_t n, const float4 *org,
                       const float4 *dir, const HitRecord *hits, float *P, float *N, int32_t *mat) {
-    k_hit_surface<<<gridFor(n, shape.numSMs, shape.blocksPerSM), kBlockThreads, shape.sceneSmemBytes, s>>>(
-        scene, n, org, dir, hits, P, N, mat);
+    if (scene.grid.enabled)
+        k_hit_surface<true><<<gridFor(n, shape.numSMs, shape.blocksPerSM), kBlockThreads, shape.sceneSmemBytes, s>>>(
+            scene, n, org, dir, hits, P, N, mat);
+    else
+        k_hit_surface<false><<<gridFor(n, shape.numSMs, shape.blocksPerSM), kBlockThreads, shape.sceneSmemBytes, s>>>(
+            scene, n, org, dir, hits, P, N, mat);
 }
 
 void launchBsdfSample(cudaStream_t s, const LaunchShape &shape, const DevMaterial *materials, uint32_t n,
@@ -562,13 +584,17 @@ cudaError_t configureKernels(LaunchShape &shape) {
             return e;
         if ((e = cudaFuncSetAttribute(k_intersect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
             return e;
-        if ((e = cudaFuncSetAttribute(k_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
+        if ((e = cudaFuncSetAttribute(k_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
+            return e;
+        if ((e = cudaFuncSetAttribute(k_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
             return e;
         if ((e = cudaFuncSetAttribute(k_intersect_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
             return e;
         if ((e = cudaFuncSetAttribute(k_intersect_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
             return e;
-        if ((e = cudaFuncSetAttribute(k_hit_surface, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
+        if ((e = cudaFuncSetAttribute(k_hit_surface<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
+            return e;
+        if ((e = cudaFuncSetAttribute(k_hit_surface<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
             return e;
     }
     auto resident = [&](auto kernel, size_t smem, int &grid) -> cudaError_t {
@@ -588,7 +614,7 @@ cudaError_t configureKernels(LaunchShape &shape) {
         return e;
     if ((e = resident(k_intersect<true>, shape.sceneSmemBytes, shape.gridIntersectGrid)) != cudaSuccess)
         return e;
-    if ((e = resident(k_shade, shape.sceneSmemBytes, shape.gridShade)) != cudaSuccess)
+    if ((e = resident(k_shade<false>, shape.sceneSmemBytes, shape.gridShade)) != cudaSuccess)
         return e;
     return resident(k_accumulate, 0, shape.gridAccumulate);
 }

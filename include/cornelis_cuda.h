@@ -215,8 +215,10 @@ int cornelis_cuda_shade(cornelis_cuda_scene *scene, size_t n, int32_t depth, con
 int cornelis_cuda_rng_uniforms(cornelis_cuda_scene *scene, uint64_t seed, size_t n, const uint32_t *pixel,
                                const uint32_t *sample, const uint32_t *block, float *out);
 
-/* Device self-test of the exact fast division (mode 0) / square root (mode 1) used by the intersection kernel against
- * the IEEE operators on n crafted operand pairs; *mismatches receives the number of results whose bits differ. */
+/* Device self-test of the hand-scheduled exact arithmetic (cornelis_b200/csrc/exact_arith.cuh) against the IEEE
+ * operators: mode 0 division, mode 1 square root (n crafted operand pairs, zeros and out-of-range operands included),
+ * mode 2 the (sqrt, reciprocal) pair of normalize over float bit patterns 0..n-1 — n = 2^32 checks EVERY float.
+ * *mismatches receives the number of results whose bits differ. */
 int cornelis_cuda_selftest_arith(cornelis_cuda_scene *scene, int mode, uint64_t n, uint32_t seed, uint64_t *mismatches);
 
 #ifdef __cplusplus

@@ -130,6 +130,8 @@ def test_exact_fast_paths(binding):
     sc = binding.Scene(scenes.cornell_box())
     assert sc.selftest_arith(0, 1 << 28, seed=7) == 0
     assert sc.selftest_arith(1, 1 << 28, seed=9) == 0
+    # normalize's sqrt + reciprocal from one rsqrt seed: exhaustive over all 2^32 float bit patterns
+    assert sc.selftest_arith(2, 1 << 32) == 0
 
 
 def test_general_planes_and_odd_rays(binding, oracle):
