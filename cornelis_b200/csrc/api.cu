@@ -110,7 +110,9 @@ struct cornelis_cuda_scene {
     bool gridBuilt = false, gridUsable = false;
     DevGrid grid{};
     uint64_t gridItems = 0;
-    DeviceBuffer<uint32_t> gridCellStart, gridCellItems;
+    DeviceBuffer<uint2> gridCellRange;
+    DeviceBuffer<float4> gridCellSpheres;
+    DeviceBuffer<uint32_t> gridCellIds;
     int smemOptin = 0;
     // wavefront state
     uint32_t width = 0, height = 0;
@@ -140,7 +142,7 @@ struct cornelis_cuda_scene {
         if (stream)
             cudaStreamSynchronize(stream);
         spheres.release(), sphereMaterial.release(), planes.release(), materials.release();
-        gridCellStart.release(), gridCellItems.release(), planeOrder.release();
+        gridCellRange.release(), gridCellSpheres.release(), gridCellIds.release(), planeOrder.release();
         for (auto &half : pool)
             for (auto &b : half)
                 b.release();
@@ -222,17 +224,24 @@ int applyAcceleration(cornelis_cuda_scene *s, int mode) {
         s->gridUsable = buildGrid(s->hostSpheres.data(), s->hostSpheres.size(), s->boxMin, s->boxMax, h);
         s->gridBuilt = true;
         if (s->gridUsable) {
-            CB_CUDA(s->gridCellStart.reserve(h.cellStart.size()));
-            CB_CUDA(s->gridCellItems.reserve(h.cellItems.size()));
-            CB_CUDA(cudaMemcpyAsync(s->gridCellStart.ptr, h.cellStart.data(), h.cellStart.size() * sizeof(uint32_t),
+            size_t const refs = h.cellIds.size();
+            CB_CUDA(s->gridCellRange.reserve(h.cellRange.size()));
+            CB_CUDA(s->gridCellSpheres.reserve(refs ? refs : 1));
+            CB_CUDA(s->gridCellIds.reserve(refs ? refs : 1));
+            CB_CUDA(cudaMemcpyAsync(s->gridCellRange.ptr, h.cellRange.data(), h.cellRange.size() * sizeof(uint2),
                                     cudaMemcpyHostToDevice, s->stream));
-            CB_CUDA(cudaMemcpyAsync(s->gridCellItems.ptr, h.cellItems.data(), h.cellItems.size() * sizeof(uint32_t),
-                                    cudaMemcpyHostToDevice, s->stream));
+            if (refs) {
+                CB_CUDA(cudaMemcpyAsync(s->gridCellSpheres.ptr, h.cellSpheres.data(), refs * sizeof(float4),
+                                        cudaMemcpyHostToDevice, s->stream));
+                CB_CUDA(cudaMemcpyAsync(s->gridCellIds.ptr, h.cellIds.data(), refs * sizeof(uint32_t),
+                                        cudaMemcpyHostToDevice, s->stream));
+            }
             CB_CUDA(cudaStreamSynchronize(s->stream));
             s->grid = h.g;
-            s->grid.cellStart = s->gridCellStart.ptr;
-            s->grid.cellItems = s->gridCellItems.ptr;
-            s->gridItems = h.cellStart.back();
+            s->grid.cellRange = s->gridCellRange.ptr;
+            s->grid.cellSpheres = s->gridCellSpheres.ptr;
+            s->grid.cellIds = s->gridCellIds.ptr;
+            s->gridItems = refs;
         }
     }
     if (wantGrid && !s->gridUsable) {

@@ -55,8 +55,9 @@ struct DevGrid {
     float margin;                  // slack (a distance) on the front-to-back termination test
     uint32_t nx, ny, nz;           // resolution
     uint32_t enabled;              // 0: scan all spheres from shared memory
-    const uint32_t *cellStart;     // nx*ny*nz + 1 offsets into cellItems
-    const uint32_t *cellItems;     // sphere indices, ascending within a cell
+    const uint2 *cellRange;        // per cell: [first, last) into the two reference arrays
+    const float4 *cellSpheres;     // per reference: a copy of the sphere (c.xyz, r^2), so a test costs one load
+    const uint32_t *cellIds;       // per reference: the sphere index, ascending within a cell
 };
 
 struct SceneView {

@@ -72,7 +72,9 @@ inline void sceneOriginBox(const cornelis_camera_desc &camera, const cornelis_sp
 // boxes, the plane rectangles and the camera eye.
 struct HostGrid {
     DevGrid g{};
-    std::vector<uint32_t> cellStart, cellItems;
+    std::vector<uint2> cellRange;      // per cell
+    std::vector<float4> cellSpheres;   // per reference
+    std::vector<uint32_t> cellIds;     // per reference
 };
 
 inline bool buildGrid(const cornelis_sphere_desc *spheres, size_t n, const double boxMin[3], const double boxMax[3],
@@ -133,6 +135,23 @@ inline bool buildGrid(const cornelis_sphere_desc *spheres, size_t n, const doubl
             first = static_cast<uint32_t>(std::min<double>(dim[a] - 1, std::max(0.0, f)));
             last = static_cast<uint32_t>(std::min<double>(dim[a] - 1, std::max(0.0, l)));
         };
+        // a sphere is listed in the cells of its padded box that come within `reach` of its centre
+        std::vector<double> reach2(n);
+        for (size_t i = 0; i < n; i++) {
+            double const r = std::fabs(static_cast<double>(spheres[i].radius));
+            double const reach = std::sqrt(r * r + eps) + delta;
+            reach2[i] = reach * reach;
+        }
+        auto touches = [&](size_t i, uint32_t x, uint32_t y, uint32_t z) {
+            uint32_t const c[3] = {x, y, z};
+            double dist2 = 0;
+            for (int a = 0; a < 3; a++) {
+                double const lo_ = gmin[a] + c[a] * cell[a], hi_ = lo_ + cell[a], p = spheres[i].center[a];
+                double const dd = p < lo_ ? lo_ - p : p > hi_ ? p - hi_ : 0.0;
+                dist2 += dd * dd;
+            }
+            return dist2 <= reach2[i] * (1.0 + 1e-9);
+        };
         std::vector<uint32_t> start(ncell + 1, 0);
         uint64_t total = 0;
         for (size_t i = 0; i < n; i++) {
@@ -145,22 +164,34 @@ inline bool buildGrid(const cornelis_sphere_desc *spheres, size_t n, const doubl
             for (uint32_t z = f[2]; z <= l[2]; z++)
                 for (uint32_t y = f[1]; y <= l[1]; y++)
                     for (uint32_t x = f[0]; x <= l[0]; x++)
-                        start[(static_cast<size_t>(z) * dim[1] + y) * dim[0] + x + 1]++;
+                        if (touches(i, x, y, z))
+                            start[(static_cast<size_t>(z) * dim[1] + y) * dim[0] + x + 1]++;
         }
         if (total > (1ull << 28))
             continue; // too many references at this resolution: coarsen
         for (size_t c = 0; c < ncell; c++)
             start[c + 1] += start[c];
-        std::vector<uint32_t> items(start[ncell] ? start[ncell] : 1), fill(start.begin(), start.end() - 1);
+        size_t const nrefs = start[ncell];
+        std::vector<uint32_t> ids(nrefs ? nrefs : 1), fill(start.begin(), start.end() - 1);
+        std::vector<float4> copies(nrefs ? nrefs : 1);
         for (size_t i = 0; i < n; i++) { // ascending sphere index within every cell
             uint32_t f[3], l[3];
             for (int a = 0; a < 3; a++)
                 range(i, a, f[a], l[a]);
+            float4 const copy = make_float4(spheres[i].center[0], spheres[i].center[1], spheres[i].center[2],
+                                            spheres[i].radius * spheres[i].radius); // as DevSphere (api.cu)
             for (uint32_t z = f[2]; z <= l[2]; z++)
                 for (uint32_t y = f[1]; y <= l[1]; y++)
                     for (uint32_t x = f[0]; x <= l[0]; x++)
-                        items[fill[(static_cast<size_t>(z) * dim[1] + y) * dim[0] + x]++] = static_cast<uint32_t>(i);
+                        if (touches(i, x, y, z)) {
+                            uint32_t const slot = fill[(static_cast<size_t>(z) * dim[1] + y) * dim[0] + x]++;
+                            ids[slot] = static_cast<uint32_t>(i);
+                            copies[slot] = copy;
+                        }
         }
+        std::vector<uint2> ranges(ncell);
+        for (size_t c = 0; c < ncell; c++)
+            ranges[c] = make_uint2(start[c], start[c + 1]);
         DevGrid &g = out.g;
         // round the grid bounds outwards, the trusted region inwards
         g.minx = std::nextafterf(static_cast<float>(gmin[0]), -INFINITY), g.maxx = std::nextafterf(static_cast<float>(gmax[0]), INFINITY);
@@ -174,8 +205,11 @@ inline bool buildGrid(const cornelis_sphere_desc *spheres, size_t n, const doubl
         g.margin = static_cast<float>(2.0 * std::sqrt(eps) * 1.001);
         g.nx = dim[0], g.ny = dim[1], g.nz = dim[2];
         g.enabled = 1;
-        out.cellStart.swap(start);
-        out.cellItems.swap(items);
+        out.cellRange.swap(ranges);
+        out.cellSpheres.swap(copies);
+        out.cellIds.swap(ids);
+        out.cellIds.resize(nrefs);
+        out.cellSpheres.resize(nrefs);
         return true;
     }
     return false;
