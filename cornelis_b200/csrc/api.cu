@@ -449,10 +449,13 @@ int cornelis_cuda_render_accumulate(cornelis_cuda_scene *s, const cornelis_rende
 
     int pipeline = p->pipeline;
     if (pipeline == CORNELIS_PIPELINE_DEFAULT) {
-        pipeline = CORNELIS_PIPELINE_PERSISTENT;
+        // Few primitives in shared memory: paths stay in registers (persistent).  Grid scenes: walks differ so much in
+        // length that warps pulling rays from the pool (wavefront, k_walk) keep their lanes busier.
+        pipeline = s->view.grid.enabled ? CORNELIS_PIPELINE_WAVEFRONT : CORNELIS_PIPELINE_PERSISTENT;
         if (const char *env = std::getenv("CORNELIS_PIPELINE"))
-            if (std::strcmp(env, "wavefront") == 0)
-                pipeline = CORNELIS_PIPELINE_WAVEFRONT;
+            pipeline = std::strcmp(env, "wavefront") == 0    ? CORNELIS_PIPELINE_WAVEFRONT
+                       : std::strcmp(env, "persistent") == 0 ? CORNELIS_PIPELINE_PERSISTENT
+                                                             : pipeline;
     }
     if (pipeline != CORNELIS_PIPELINE_WAVEFRONT && pipeline != CORNELIS_PIPELINE_PERSISTENT)
         return fail(CORNELIS_ERR_INVALID_ARGUMENT, "unknown pipeline");
@@ -572,7 +575,7 @@ int cornelis_cuda_render_accumulate(cornelis_cuda_scene *s, const cornelis_rende
                 }
                 profiled++;
             }
-            launches += 5;
+            launches += (s->view.grid.enabled && s->shape.walkPull) ? 6 : 5;
             cur ^= 1;
         }
         CB_CUDA(cudaMemcpyAsync(s->hostControl, s->control.ptr, sizeof(Control), cudaMemcpyDeviceToHost, st));

@@ -125,6 +125,7 @@ struct Control {
     unsigned long long shaded;     // hits shaded
     unsigned long long iterations; // passes
     unsigned long long contributions; // finished paths added to the framebuffer
+    unsigned long long walkCursor;    // grid scenes: next pooled ray to be claimed by k_walk (reset by k_plan)
 };
 
 struct RenderConfig {

@@ -23,6 +23,7 @@ __global__ void k_plan(Control *ctl, RenderConfig cfg) {
     ctl->nSurvive = 0;
     ctl->nHit = 0;
     ctl->nFinished = 0;
+    ctl->walkCursor = 0;
     ctl->rays += survivors + gen;
     ctl->iterations += (survivors + gen) ? 1 : 0;
 }
@@ -89,6 +90,115 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_INTERSECT_MIN_BLOCKS) 
         if (valid) {
             hit = t < INFINITY; // Render.cpp:146
             hits[i] = HitRecord{t, prim};
+            if (!hit) {
+                radiance = pool.rad[i];
+                finish = radiance.x != 0.0f || radiance.y != 0.0f || radiance.z != 0.0f;
+            }
+        }
+        AppendSlots const slot = blockAppend2(hit, finish, &ctl->nHit, &ctl->nFinished, scratch);
+        if (hit)
+            hitQueue[slot.a] = i;
+        if (finish)
+            finished[slot.b] = FinishedPath{radiance.x, radiance.y, radiance.z, __float_as_uint(radiance.w)};
+    }
+}
+
+// ----------------------------------------------------------------------------------- intersect, grid scenes --
+
+// Walking the grid costs anything from a handful to a hundred steps per ray, and with one ray per thread a warp waits
+// for its longest walk: ncu on the one-ray-per-lane form shows 7.7 of 32 lanes active per instruction on config 4
+// (profiles/r1_diet).  k_walk is a persistent kernel of warps that PULL rays: a lane whose walk is over takes the
+// next pooled ray (a warp claims indices 256 at a time with one atomic, like the persistent pipeline's camera paths),
+// so all lanes keep stepping until the pool is drained.  Refills are batched — they run when a quarter of the warp is
+// idle — because setting up a walk (plane tests, clipping, DDA) is itself ~150 instructions.  Only the hit records are
+// written here; k_compact_hits builds the queues (compaction #1) in a streaming pass.
+constexpr unsigned kWalkClaim = 256;  // rays a warp claims per atomic
+constexpr unsigned kWalkRefill = 8;   // idle lanes that trigger a refill
+
+#ifndef CORNELIS_WALK_MIN_BLOCKS
+#define CORNELIS_WALK_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(kBlockThreads, CORNELIS_WALK_MIN_BLOCKS)
+    k_walk(Control *ctl, SceneView scene, PathPool pool, HitRecord *__restrict__ hits) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SharedScene const sh = stageScene<true>(scene, smem, false);
+    constexpr unsigned kFull = 0xffffffffu;
+    unsigned const lane = threadIdx.x & 31u;
+    unsigned const below = (1u << lane) - 1u;
+    unsigned long long const n = ctl->nIn;
+    unsigned long long stashNext = 0, stashEnd = 0;
+    bool walking = false, exhausted = false;
+    uint32_t index = 0;
+    V3 o{0.f, 0.f, 0.f}, d{0.f, 0.f, 0.f};
+    float t = INFINITY;
+    int32_t prim = -1;
+    GridWalk w{};
+    for (;;) {
+        unsigned const idleMask = __ballot_sync(kFull, !walking && !exhausted);
+        unsigned const walkMask = __ballot_sync(kFull, walking);
+        if (idleMask && (__popc(idleMask) >= kWalkRefill || walkMask == 0u)) {
+            unsigned const count = __popc(idleMask);
+            unsigned const avail = static_cast<unsigned>(stashEnd - stashNext);
+            unsigned long long fresh = 0;
+            if (count > avail) {
+                if (lane == 0)
+                    fresh = atomicAdd(&ctl->walkCursor, static_cast<unsigned long long>(kWalkClaim));
+                fresh = __shfl_sync(kFull, fresh, 0);
+            }
+            unsigned const rank = __popc(idleMask & below);
+            unsigned long long const mine = rank < avail ? stashNext + rank : fresh + (rank - avail);
+            if (count > avail) {
+                stashNext = fresh + (count - avail);
+                stashEnd = fresh + kWalkClaim;
+            } else {
+                stashNext += count;
+            }
+            if (!walking && !exhausted) {
+                if (mine >= n) {
+                    exhausted = true;
+                } else {
+                    index = static_cast<uint32_t>(mine);
+                    float4 const o4 = pool.org[index], d4 = pool.dir[index];
+                    o = V3{o4.x, o4.y, o4.z};
+                    d = V3{d4.x, d4.y, d4.z};
+                    t = INFINITY; // IntersectionData::reset, Geometry.cpp:7-12
+                    prim = -1;
+                    walking = gridWalkBegin(w, o, d, scene, sh.planes, t, prim);
+                    if (!walking)
+                        hits[index] = HitRecord{t, prim}; // decided without a walk (degenerate, outside the grid, ...)
+                }
+            }
+        } else if (walkMask == 0u) {
+            break; // nothing walking, nothing left to claim
+        }
+        // a burst of steps; stop early when enough lanes have finished to make a refill worthwhile
+#pragma unroll 1
+        for (int burst = 0; burst < 16; burst++) {
+            if (walking) {
+                walking = gridWalkStep(w, o, d, scene.grid, t, prim);
+                if (!walking)
+                    hits[index] = HitRecord{t, prim};
+            }
+            if (__popc(__ballot_sync(kFull, !walking && !exhausted)) >= kWalkRefill)
+                break;
+        }
+    }
+}
+
+// Compaction #1 for grid scenes (Render.cpp:142-149): hits to the hit queue, misses that carry radiance to the finished
+// queue — the tail of k_intersect as a streaming pass over the hit records.
+__global__ void __launch_bounds__(kBlockThreads) k_compact_hits(Control *ctl, PathPool pool,
+                                                                const HitRecord *__restrict__ hits,
+                                                                uint32_t *__restrict__ hitQueue,
+                                                                FinishedPath *__restrict__ finished) {
+    __shared__ uint32_t scratch[2][kWarpsPerBlock + 1];
+    uint32_t const n = ctl->nIn;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        uint32_t const i = base + threadIdx.x;
+        bool hit = false, finish = false;
+        float4 radiance = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) {
+            hit = hits[i].t < INFINITY; // Render.cpp:146
             if (!hit) {
                 radiance = pool.rad[i];
                 finish = radiance.x != 0.0f || radiance.y != 0.0f || radiance.z != 0.0f;
@@ -471,10 +581,15 @@ void launchRaygen(cudaStream_t s, const LaunchShape &shape, const Control *ctl, 
 
 void launchIntersect(cudaStream_t s, const LaunchShape &shape, Control *ctl, const SceneView &scene,
                      const PathPool &pool, HitRecord *hits, uint32_t *hitQueue, FinishedPath *finished) {
-    if (scene.grid.enabled)
-        k_intersect<true><<<shape.gridIntersectGrid, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, scene, pool, hits,
-                                                                                               hitQueue, finished);
-    else
+    if (scene.grid.enabled) {
+        if (shape.walkPull) {
+            k_walk<<<shape.gridWalk, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, scene, pool, hits);
+            k_compact_hits<<<shape.gridAccumulate, kBlockThreads, 0, s>>>(ctl, pool, hits, hitQueue, finished);
+        } else {
+            k_intersect<true><<<shape.gridIntersectGrid, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, scene, pool, hits,
+                                                                                                   hitQueue, finished);
+        }
+    } else
         k_intersect<false><<<shape.gridIntersect, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, scene, pool, hits,
                                                                                             hitQueue, finished);
 }
@@ -584,6 +699,8 @@ cudaError_t configureKernels(LaunchShape &shape) {
             return e;
         if ((e = cudaFuncSetAttribute(k_intersect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
             return e;
+        if ((e = cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
+            return e;
         if ((e = cudaFuncSetAttribute(k_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
             return e;
         if ((e = cudaFuncSetAttribute(k_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
@@ -614,6 +731,10 @@ cudaError_t configureKernels(LaunchShape &shape) {
         return e;
     if ((e = resident(k_intersect<true>, shape.sceneSmemBytes, shape.gridIntersectGrid)) != cudaSuccess)
         return e;
+    if ((e = resident(k_walk, shape.sceneSmemBytes, shape.gridWalk)) != cudaSuccess)
+        return e;
+    if (const char *env = std::getenv("CORNELIS_WALK_PULL"))
+        shape.walkPull = std::atoi(env) != 0;
     if ((e = resident(k_shade<false>, shape.sceneSmemBytes, shape.gridShade)) != cudaSuccess)
         return e;
     return resident(k_accumulate, 0, shape.gridAccumulate);

@@ -14,7 +14,8 @@ struct LaunchShape {
     int blocksPerSM = 4;      // resident 256-thread CTAs per SM for the stage entry points
     // Persistent grids: numSMs x (CTAs of that kernel resident per SM, from the occupancy calculator), so every CTA
     // is resident for the whole launch and the grid-stride loops split the pool evenly.
-    int gridRaygen = 592, gridIntersect = 592, gridIntersectGrid = 592, gridShade = 592, gridAccumulate = 592;
+    int gridRaygen = 592, gridIntersect = 592, gridIntersectGrid = 592, gridWalk = 592, gridShade = 592, gridAccumulate = 592;
+    bool walkPull = true;     // grid scenes: k_walk (warps pull rays) + k_compact_hits instead of one ray per thread
     size_t sceneSmemBytes = 0;
 };
 

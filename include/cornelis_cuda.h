@@ -79,11 +79,12 @@ enum {
 };
 
 enum {
-    CORNELIS_PIPELINE_DEFAULT = 0,
+    CORNELIS_PIPELINE_DEFAULT = 0,   /* persistent for scenes scanned from shared memory, wavefront for grid scenes */
     CORNELIS_PIPELINE_WAVEFRONT = 1, /* raygen -> intersect(+compact) -> shade(+compact) -> accumulate kernels over
-                                        a path pool in HBM; works for any scene size */
+                                        a path pool in HBM; with the grid the intersect stage is a kernel of warps
+                                        that pull rays from the pool plus a streaming compaction pass */
     CORNELIS_PIPELINE_PERSISTENT = 2 /* the same stage functions with each path held in its thread's registers and
-                                        finished lanes refilled by a warp-level claim; the default */
+                                        finished lanes refilled by a warp-level claim */
 };
 
 typedef struct cornelis_render_params {

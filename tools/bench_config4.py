@@ -31,8 +31,8 @@ out = {"workload": f"{args.spheres} spheres + floor, 64 materials, {W}x{H}, {arg
        "acceleration": scene.acceleration()}
 scene.render_accumulate(W, H, 4, max_depth=64)  # warm-up
 for name, pipeline in (("persistent", binding.PIPELINE_PERSISTENT), ("wavefront", binding.PIPELINE_WAVEFRONT)):
-    st = scene.render_accumulate(W, H, args.spp, max_depth=64, pipeline=pipeline)
-    out[name] = {"msamples_per_s": st["pixel_samples"] / st["gpu_ms"] / 1e3, "mrays_per_s": st["rays"] / st["gpu_ms"] / 1e3,
+    st = scene.render_accumulate(W, H, args.spp, max_depth=64, pipeline=pipeline, stage_timing=True)
+    out[name] = {"stage_ms_per_pass": {k: st[k] for k in ("raygen_ms", "intersect_ms", "shade_ms", "accumulate_ms")},"msamples_per_s": st["pixel_samples"] / st["gpu_ms"] / 1e3, "mrays_per_s": st["rays"] / st["gpu_ms"] / 1e3,
                  "gpu_ms": st["gpu_ms"], "rays_per_sample": st["rays"] / st["pixel_samples"], "max_depth": st["max_depth"],
                  "kernel_launches": st["kernel_launches"]}
 if not args.no_exhaustive:
