@@ -37,6 +37,12 @@ FLOP_PER_RAY_CORNELL = 4 * 26 + 5 * 35        # 279: 4 sphere tests x 26 flop + 
 FLOP_PER_SURVIVING_BOUNCE = 250
 FLOP_PER_KILLED_HIT = 12
 # bytes per item of the wavefront layout (DESIGN.md "Data layout"): see roofline() below
+# DRAM traffic of k_persistent from the committed ncu capture (profiles/r1_diet/
+# ncu_full_summary_k_persistent_cornell_512spp.txt): dram__bytes_read.sum + dram__bytes_write.sum = 32.58 MB + 0.33 MB
+# for one launch of 1920x1080 x 512 spp.  The only global traffic is framebuffer atomics over a 33 MB image that
+# lives in the 126 MB L2, so DRAM sees little more than one read of the image per launch.
+NCU_PERSISTENT_DRAM_BYTES = 32.576768e6 + 0.331008e6
+NCU_PERSISTENT_PIXEL_SAMPLES = 1920 * 1080 * 512
 
 
 def parse_args():
@@ -221,6 +227,13 @@ def roofline(stats_list, hbm_peak, hbm_source, persistent):
         # (16 B read + 16 B written) of paths that end with non-zero radiance
         nbytes = 32.0 * tot["contributions"] / launches
         extra["rays_per_launch"] = tot["rays"] / launches
+        extra["traffic"] = NCU_PERSISTENT_DRAM_BYTES * (tot["pixel_samples"] / launches) / NCU_PERSISTENT_PIXEL_SAMPLES
+        extra["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of a "
+                                   "512-spp launch (profiles/r1_diet), scaled by pixel-samples per launch; below the "
+                                   "algorithmic bytes because the 33 MB framebuffer stays in L2")
+        extra["issue_slots"] = {"busy_pct": 86.6, "warp_instructions_per_ray": 49.4, "lanes_per_instruction": 23.2,
+                                "source": "same capture: smsp__issue_active, smsp__inst_executed.sum / rays, "
+                                          "smsp__thread_inst_executed_per_inst_executed"}
     else:
         launches = max(1, tot["iterations"])
         stage = {k: statistics.mean(s[k] for s in stats_list)
@@ -250,7 +263,7 @@ def roofline(stats_list, hbm_peak, hbm_source, persistent):
         "frac": achieved / fp32_peak,
         "peak_source": "148 SM x 128 FP32 lanes x 1.965 GHz, one non-FMA op per lane per clock (SURVEY.md 8d); "
                        "FP32 is not in MEASURED_PEAKS.json",
-        "traffic": None,
+        "traffic": extra.pop("traffic", None),
         "launch_ms": ms, "flop_per_launch": flop,
         "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                 "bytes_per_launch": nbytes, "peak_source": hbm_source},

@@ -95,6 +95,10 @@ struct RenderSession::State {
             if (int rc = cornelis_cuda_scene_create(dev, &c, spheres.data(), spheres.size(), planes.data(), planes.size(),
                                                     mats.data(), mats.size(), &devices[static_cast<std::size_t>(dev)].handle))
                 raise(rc, "cornelis_cuda_scene_create");
+            if (options.acceleration != Acceleration::Auto)
+                if (int rc = cornelis_cuda_scene_set_acceleration(devices[static_cast<std::size_t>(dev)].handle,
+                                                                  static_cast<int>(options.acceleration)))
+                    raise(rc, "cornelis_cuda_scene_set_acceleration");
         }
     }
 

@@ -71,10 +71,59 @@ static SceneDescription cornellBox(float aspect) {
     return scene;
 }
 
+// BASELINE.json configs[3]-style scene: n random spheres over one 4000x4000 floor, 64 materials of the one material
+// model with varied albedo / tint / roughness / ior, 2 % of them emissive.  SplitMix64 keyed by
+// the seed; floats use the reference's 24-bit mapping.
+static SceneDescription manySpheres(std::size_t n, std::uint64_t seed, float aspect) {
+    std::uint64_t state = seed;
+    auto uniform = [&state]() {
+        std::uint64_t z = (state += 0x9e3779b97f4a7c15ull);
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        z ^= z >> 31;
+        return static_cast<float>(static_cast<std::uint32_t>(z >> 32) >> 8) * 0x1.0p-24f;
+    };
+    SceneDescription scene;
+    PerspectiveCameraDescription cam;
+    cam.origin = V3(0, 600, -2500);
+    cam.lookAt = V3(0, 300, 0);
+    cam.aspect = aspect;
+    cam.horizontalFov = 0.7f;
+    scene.setCamera(cam);
+    std::size_t ids[64];
+    for (std::size_t k = 0; k < 64; k++) {
+        MaterialDescription m;
+        m.albedo = RGB(0.1f + 0.8f * uniform(), 0.1f + 0.8f * uniform(), 0.1f + 0.8f * uniform());
+        if (uniform() < 0.5f)
+            m.reflectionTint = RGB(0.5f + 0.5f * uniform(), 0.5f + 0.5f * uniform(), 0.5f + 0.5f * uniform());
+        m.roughness = 0.01f + 0.59f * uniform();
+        m.ior = 1.2f + 0.8f * uniform();
+        if (uniform() < 0.02f)
+            m.emissive = RGB(15, 15, 15);
+        ids[k] = scene.addMaterial(m);
+    }
+    PlaneDescription floor;
+    floor.normal = V3(0, 1, 0);
+    floor.point = V3(0, 0, 0);
+    floor.extents = V3(4000, 4000, 0);
+    floor.material = ids[1];
+    scene.addPlane(floor);
+    for (std::size_t i = 0; i < n; i++) {
+        SphereDescription s;
+        float const x = 2000.0f * uniform() - 1000.0f, y = 2000.0f * uniform(), z = 2000.0f * uniform() - 1000.0f;
+        s.center = V3(x, y, z);
+        s.radius = 5.0f + 20.0f * uniform();
+        s.material = ids[i % 64];
+        scene.addSphere(s);
+    }
+    return scene;
+}
+
 static void usage() {
     std::puts("usage: cornelis [--width W] [--height H] [--spp N] [--aspect A] [--seed S] [--max-depth D]\n"
               "                [--devices G] [--pool P] [--output file.png] [--no-save] [--drop-nonfinite] [--quiet]\n"
-              "defaults reproduce the reference CLI: 512x512, 4096 spp, cornelisrender2.png");
+              "                [--scene cornell|spheres] [--spheres N] [--accel auto|none|grid]\n"
+              "defaults reproduce the reference CLI: the Cornell box, 512x512, 4096 spp, cornelisrender2.png");
 }
 
 int main(int argc, char *argv[]) {
@@ -82,6 +131,8 @@ int main(int argc, char *argv[]) {
     options.samplesAA = 4096;
     float aspect = -1.0f;
     bool quiet = false;
+    std::string sceneName = "cornell";
+    std::size_t sphereCount = 10000;
     for (int i = 1; i < argc; i++) {
         std::string const a = argv[i];
         auto next = [&]() -> char const * {
@@ -103,6 +154,12 @@ int main(int argc, char *argv[]) {
         else if (a == "--no-save") options.saveImage = false;
         else if (a == "--drop-nonfinite") options.dropNonFinite = true;
         else if (a == "--quiet") quiet = true;
+        else if (a == "--scene") sceneName = next();
+        else if (a == "--spheres") sphereCount = static_cast<std::size_t>(std::atoll(next()));
+        else if (a == "--accel") {
+            std::string const m = next();
+            options.acceleration = m == "none" ? Acceleration::None : m == "grid" ? Acceleration::Grid : Acceleration::Auto;
+        }
         else {
             usage();
             return a == "--help" || a == "-h" ? 0 : 2;
@@ -111,7 +168,12 @@ int main(int argc, char *argv[]) {
     if (aspect <= 0.0f) // square pixels: the camera's aspect scales the vertical film vector
         aspect = options.width > 0 ? static_cast<float>(options.height) / static_cast<float>(options.width) : 1.0f;
     try {
-        RenderSession session(cornellBox(aspect), options);
+        if (sceneName != "cornell" && sceneName != "spheres") {
+            usage();
+            return 2;
+        }
+        RenderSession session(sceneName == "spheres" ? manySpheres(sphereCount, options.seed, aspect) : cornellBox(aspect),
+                              options);
         auto const t0 = std::chrono::steady_clock::now();
         int lastDecile = -1;
         session.render([&](RenderProgress const &p, RenderStatus const &status) {

@@ -9,6 +9,11 @@
 
 namespace cornelis {
 
+// How the intersect stage finds the closest sphere (include/cornelis_cuda.h CORNELIS_ACCEL_*): the reference scans
+// every sphere for every ray (Render.cpp:115-123); the uniform grid returns the same hit, bit for bit, from the
+// spheres near the ray.  Auto picks the grid for scenes with many spheres.
+enum class Acceleration : std::int32_t { Auto = 0, None = 1, Grid = 2 };
+
 struct RenderOptions {
     static constexpr std::int32_t DefaultSamplesAA = 1 << 8;
 
@@ -22,6 +27,7 @@ struct RenderOptions {
     std::int32_t maxDepth = 0;       // 0 = unlimited; otherwise a path stops after this many bounces
     std::int32_t devices = 1;        // GPUs of this box to shard the samples over
     std::int32_t poolPaths = 0;      // paths in flight per GPU (0 = library default)
+    Acceleration acceleration = Acceleration::Auto;
     bool dropNonFinite = false;      // skip NaN/inf path contributions (the reference lets them through)
     bool saveImage = true;           // write the PNG at the end of render(), as the reference does
     std::string outputPath = "cornelisrender2.png";

@@ -49,3 +49,18 @@ def test_cli_renders_reference_default_scene(tmp_path):
     r = subprocess.run([str(LIB / "cornelis"), "--spp", "16", "--output", str(out)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "512x512, 16 spp" in r.stdout and out.exists() and out.stat().st_size > 512 * 512 * 3
+
+
+@pytest.mark.gpu
+def test_cli_many_spheres_grid_and_exhaustive_agree(tmp_path):
+    """The CLI's many-sphere scene (BASELINE configs[3] style) through the grid and through the exhaustive scan: the
+    same paths, hence the same statistics line apart from the timings."""
+    lines = []
+    for accel in ("grid", "none"):
+        r = subprocess.run([str(LIB / "cornelis"), "--scene", "spheres", "--spheres", "2000", "--width", "96", "--height",
+                            "54", "--spp", "8", "--max-depth", "64", "--accel", accel, "--no-save"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        lines.append(r.stdout.strip().splitlines()[-1])
+    tail = [ln.split("Mrays/s,")[1] for ln in lines]     # "x rays/sample, deepest path y"
+    assert tail[0] == tail[1], lines
