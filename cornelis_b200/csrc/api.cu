@@ -387,6 +387,7 @@ int cornelis_cuda_scene_create(int device, const cornelis_camera_desc *camera, c
     s->hostSpheres.assign(spheres, spheres + n_spheres);
     sceneOriginBox(*camera, spheres, n_spheres, hp.data(), n_planes, s->boxMin, s->boxMax);
     s->smemOptin = smemOptin;
+    s->shape.smemOptin = static_cast<size_t>(smemOptin);
     if (int rc = applyAcceleration(s, CORNELIS_ACCEL_AUTO))
         return rc;
 

@@ -164,17 +164,25 @@ CB_HD V3 pixelRayDirection(const DevCamera &c, uint32_t i, uint32_t j, float dx,
 
 // ----------------------------------------------------------------------------------------------- shade body --
 
-// accumulateAndBounce for one ray (Render.cpp:173-216).  u = (RR draw, x0, x1, x2).
-// Returns true if the path survives; org/dir/thr are then the next ray and the updated throughput.
-__device__ __forceinline__ bool shadeBounce(const DevMaterial &mat, V3 P, V3 N, uint32_t depth, float u0, float x0,
-                                            float x1, float x2, V3 &org, V3 &dir, RGBf &thr, RGBf &rad) {
-    V3 const wOut = -dir;                                                   // Render.cpp:174
-    float const prob = russianRouletteFactor(thr.r, thr.g, thr.b, depth);   // Render.cpp:182
+// accumulateAndBounce for one ray (Render.cpp:173-216), in two halves so that the persistent pipeline can park the
+// survivors of Russian roulette between them (persistent.cu).
+//
+// First half, Render.cpp:174-192: emission is added before the roulette test (Render.cpp:187), then the path survives
+// with probability `prob`.  u0 = the RR draw.
+__device__ __forceinline__ bool shadeRoulette(const DevMaterial &mat, uint32_t depth, float u0, RGBf thr, RGBf &rad,
+                                              float &prob) {
+    prob = russianRouletteFactor(thr.r, thr.g, thr.b, depth);              // Render.cpp:182
     rad.r += thr.r * mat.er;                                                // Render.cpp:187, :67-69
     rad.g += thr.g * mat.eg;
     rad.b += thr.b * mat.eb;
-    if (prob < u0)                                                          // Render.cpp:189
-        return false;
+    return !(prob < u0);                                                    // Render.cpp:189
+}
+
+// Second half, Render.cpp:194-213: sample the layered BSDF at the hit, build the next ray and update the throughput.
+// dir is the incoming ray's direction on entry and the sampled direction on exit.
+__device__ __forceinline__ void shadeScatter(const DevMaterial &mat, V3 P, V3 N, float prob, float x0, float x1, float x2,
+                                             V3 &org, V3 &dir, RGBf &thr) {
+    V3 const wOut = -dir;                                                   // Render.cpp:174
     Basis const basis = constructBasis(N);                                  // Render.cpp:194
     V3 wIn;
     float pdf;
@@ -199,6 +207,16 @@ __device__ __forceinline__ bool shadeBounce(const DevMaterial &mat, V3 P, V3 N, 
         thr.g *= ng / denom;
         thr.b *= nb / denom;
     }
+}
+
+// Both halves back to back.  u = (RR draw, x0, x1, x2).
+// Returns true if the path survives; org/dir/thr are then the next ray and the updated throughput.
+__device__ __forceinline__ bool shadeBounce(const DevMaterial &mat, V3 P, V3 N, uint32_t depth, float u0, float x0,
+                                            float x1, float x2, V3 &org, V3 &dir, RGBf &thr, RGBf &rad) {
+    float prob;
+    if (!shadeRoulette(mat, depth, u0, thr, rad, prob))
+        return false;
+    shadeScatter(mat, P, N, prob, x0, x1, x2, org, dir, thr);
     return true;
 }
 

@@ -171,16 +171,215 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
     }
 }
 
+// ---------------------------------------------------------------------------------------- queued variant --
+//
+// ncu on k_persistent (profiles/r1_diet) shows the issue slots 86 % busy but only 23 of 32 lanes active per
+// instruction: the BSDF half of a bounce runs with the 71 % of the lanes whose ray hit something AND survived Russian
+// roulette, and the camera-ray code with the 29 % that need a new path.  k_persistent_queued parks the roulette
+// survivors in a WARP-PRIVATE shared-memory queue (compaction #2 of the reference, Render.cpp:215-217, as a stack of
+// 80-byte records) and runs the BSDF half only on full batches of 32; when fewer than 32 survivors are parked every
+// lane is free, so the warp generates 32 camera rays (32 consecutive pixels of one sample index: a coherent packet).
+// Every stage — camera rays, intersect, BSDF — therefore runs with all 32 lanes; only the short roulette half runs at
+// the hit rate.  A record is five float4 in SoA order (slot-major within a chunk: a warp's 128-bit accesses are
+// consecutive and conflict-free):
+//     org.xyz | t      dir.xyz | prim      thr.rgb | pixel      rad.rgb | sample << 8 | depth      x0 x1 x2 | prob
+// P, N and the material are re-derived from (org, dir, t, prim) when the record is popped, as in the wavefront shade
+// kernel.  No block barrier anywhere: the queue belongs to one warp (__syncwarp orders its lanes' accesses).
+constexpr uint32_t kQueueSlots = 64;  // a pop leaves fewer than 32 records, a push adds at most 32
+constexpr uint32_t kQueueChunks = 5;
+constexpr size_t kQueueBytesPerWarp = kQueueSlots * kQueueChunks * sizeof(float4);
+
 template <bool kGrid>
-static cudaError_t configureOne(const LaunchShape &shape, int &grid) {
+__global__ void __launch_bounds__(kBlockThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
+    k_persistent_queued(RenderConfig cfg, SceneView scene, unsigned long long *__restrict__ cursor,
+                        unsigned long long limit, float4 *__restrict__ accum, float4 *__restrict__ accum2,
+                        bool dropNonFinite, Control *__restrict__ ctl, uint32_t queueOffset) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SharedScene const sh = stageScene<kGrid>(scene, smem, true);
+    constexpr unsigned kFull = 0xffffffffu;
+    unsigned const lane = threadIdx.x & 31u;
+    unsigned const below = (1u << lane) - 1u;
+    float4 *const queue = reinterpret_cast<float4 *>(smem + queueOffset) + (threadIdx.x >> 5) * (kQueueSlots * kQueueChunks);
+
+    uint32_t parked = 0;        // records in the queue (warp-uniform)
+    bool camerasLeft = true;    // warp-uniform: the camera-path range is not exhausted yet
+    // warp-private stash of claimed camera-path indices [stashNext, stashEnd), always a multiple of 32 long
+    unsigned long long stashNext = 0, stashEnd = 0;
+    uint32_t stashPix = 0, stashSmp = 0; // (pixel, local sample) of stashNext
+    uint32_t rays = 0, shaded = 0, started = 0, deepest = 0, contributed = 0;
+
+    for (;;) {
+        bool alive = false;
+        V3 org{0.f, 0.f, 0.f}, dir{0.f, 0.f, 0.f};
+        RGBf thr{0.f, 0.f, 0.f}, rad{0.f, 0.f, 0.f};
+        uint32_t pixel = 0, sample = 0, depth = 0;
+        if (parked >= 32u || (!camerasLeft && parked != 0u)) {
+            // ---- second half of accumulateAndBounce (Render.cpp:194-213) for a batch of parked survivors ----
+            uint32_t const n = parked < 32u ? parked : 32u, base = parked - n;
+            if (lane < n) {
+                uint32_t const slot = base + lane;
+                float4 const q0 = queue[slot], q1 = queue[kQueueSlots + slot], q2 = queue[2 * kQueueSlots + slot],
+                             q3 = queue[3 * kQueueSlots + slot], q4 = queue[4 * kQueueSlots + slot];
+                org = V3{q0.x, q0.y, q0.z};
+                dir = V3{q1.x, q1.y, q1.z};
+                thr = RGBf{q2.x, q2.y, q2.z};
+                rad = RGBf{q3.x, q3.y, q3.z};
+                pixel = __float_as_uint(q2.w);
+                uint32_t const sd = __float_as_uint(q3.w);
+                sample = sd >> 8;
+                depth = sd & 255u;
+                V3 P, N;
+                uint32_t material;
+                hitSurface(org, dir, q0.w, static_cast<int32_t>(__float_as_uint(q1.w)), sh.spheres, sh.sphereMaterial,
+                           scene.nSpheres, sh.planes, P, N, material);
+                shadeScatter(sh.materials[material], P, N, q4.w, q4.x, q4.y, q4.z, org, dir, thr);
+                alive = true;
+            }
+            parked = base;
+            __syncwarp(); // the slots read here are overwritten by this iteration's pushes
+        } else if (camerasLeft) {
+            // ---- generateCameraRays (Render.cpp:85-100) for 32 consecutive camera paths ----
+            if (stashNext == stashEnd) { // one atomic per kClaim paths per warp; one 64-bit division per refill
+                unsigned long long fresh = 0;
+                uint32_t freshPix = 0, freshSmp = 0;
+                if (lane == 0) {
+                    fresh = atomicAdd(cursor, kClaim);
+                    unsigned long long const q = fresh / cfg.npixels;
+                    freshSmp = static_cast<uint32_t>(q);
+                    freshPix = static_cast<uint32_t>(fresh - q * cfg.npixels);
+                }
+                stashNext = __shfl_sync(kFull, fresh, 0);
+                stashEnd = stashNext + kClaim;
+                stashPix = __shfl_sync(kFull, freshPix, 0);
+                stashSmp = __shfl_sync(kFull, freshSmp, 0);
+            }
+            unsigned long long const index = stashNext + lane;
+            uint32_t newPixel = stashPix + lane, newSample = stashSmp;
+            while (newPixel >= cfg.npixels) { // runs at most once unless the frame has fewer than 32 pixels
+                newPixel -= cfg.npixels;
+                newSample++;
+            }
+            stashNext += 32u;
+            stashPix += 32u;
+            while (stashPix >= cfg.npixels) {
+                stashPix -= cfg.npixels;
+                stashSmp++;
+            }
+            camerasLeft = stashNext < limit; // the cursor only grows: once past the limit, always past it
+            if (index < limit) {
+                pixel = newPixel;
+                sample = cfg.firstSample + newSample;
+                uint32_t const j = fastDivide(pixel, cfg.byWidth), i = pixel - j * cfg.width;
+                Philox4 const r = philox4x32_10(pixel, sample, 0u, 0u, cfg.keys);
+                dir = pixelRayDirection(scene.camera, i, j, cfg.dx, cfg.dy, uniformFromBits(r.v[0]),
+                                        uniformFromBits(r.v[1]));
+                org = V3{scene.camera.ex, scene.camera.ey, scene.camera.ez};
+                thr = RGBf{1.0f, 1.0f, 1.0f}; // Render.cpp:58
+                rad = RGBf{0.0f, 0.0f, 0.0f}; // Render.cpp:60
+                alive = true;
+                started++;
+            }
+            if (!__any_sync(kFull, alive))
+                continue; // this claim lay past the limit: drain the queue, or stop
+        } else {
+            break; // no camera paths left and nothing parked
+        }
+
+        // ---- intersect (Render.cpp:110-150) ----
+        float t = INFINITY; // IntersectionData::reset, Geometry.cpp:7-12
+        int32_t prim = -1;
+        closestHitScene<kGrid>(alive, org, dir, sh, scene, t, prim);
+
+        // ---- first half of accumulateAndBounce (Render.cpp:174-192): emission, Russian roulette ----
+        bool finished = false, park = false;
+        float prob = 0.0f, x0 = 0.0f, x1 = 0.0f, x2 = 0.0f;
+        if (alive) {
+            rays++;
+            if (!(t < INFINITY)) { // Render.cpp:146: misses leave the active list
+                finished = true;
+            } else {
+                uint32_t const material = static_cast<uint32_t>(prim) < scene.nSpheres
+                                              ? sh.sphereMaterial[prim]
+                                              : sh.planes[prim - static_cast<int32_t>(scene.nSpheres)].material;
+                Philox4 const r = philox4x32_10(pixel, sample, depth + 1u, 0u, cfg.keys);
+                bool const survives =
+                    shadeRoulette(sh.materials[material], depth, uniformFromBits(r.v[0]), thr, rad, prob);
+                x0 = uniformFromBits(r.v[1]), x1 = uniformFromBits(r.v[2]), x2 = uniformFromBits(r.v[3]);
+                shaded++;
+                depth = depth < 255u ? depth + 1u : 255u;
+                deepest = depth > deepest ? depth : deepest;
+                finished = !survives || (cfg.maxDepth && depth >= cfg.maxDepth);
+                park = !finished;
+            }
+        }
+        // ---- compaction #2 (Render.cpp:215-217): survivors are pushed onto the warp's queue ----
+        unsigned const parkMask = __ballot_sync(kFull, park);
+        if (park) {
+            uint32_t const slot = parked + __popc(parkMask & below);
+            queue[slot] = make_float4(org.x, org.y, org.z, t);
+            queue[kQueueSlots + slot] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(static_cast<uint32_t>(prim)));
+            queue[2 * kQueueSlots + slot] = make_float4(thr.r, thr.g, thr.b, __uint_as_float(pixel));
+            queue[3 * kQueueSlots + slot] = make_float4(rad.r, rad.g, rad.b, __uint_as_float((sample << 8) | depth));
+            queue[4 * kQueueSlots + slot] = make_float4(x0, x1, x2, prob);
+        }
+        parked += __popc(parkMask);
+        __syncwarp();
+        // ---- per-pixel accumulation (Render.cpp:245-248) ----
+        if (finished) {
+            bool const nonZero = rad.r != 0.0f || rad.g != 0.0f || rad.b != 0.0f;
+            bool const finite = isfinite(rad.r) && isfinite(rad.g) && isfinite(rad.b);
+            contributed += nonZero ? 1u : 0u;
+            if (nonZero && (finite || !dropNonFinite)) {
+                atomicAdd(&accum[pixel], make_float4(rad.r, rad.g, rad.b, 1.0f));
+                if (accum2)
+                    atomicAdd(&accum2[pixel], make_float4(rad.r * rad.r, rad.g * rad.g, rad.b * rad.b, 0.0f));
+            }
+        }
+    }
+
+    // statistics: one set of atomics per warp
+    rays = __reduce_add_sync(kFull, rays);
+    shaded = __reduce_add_sync(kFull, shaded);
+    started = __reduce_add_sync(kFull, started);
+    contributed = __reduce_add_sync(kFull, contributed);
+    deepest = __reduce_max_sync(kFull, deepest);
+    if (lane == 0) {
+        atomicAdd(&ctl->rays, static_cast<unsigned long long>(rays));
+        atomicAdd(&ctl->shaded, static_cast<unsigned long long>(shaded));
+        atomicAdd(&ctl->cursor, static_cast<unsigned long long>(started)); // camera paths actually started
+        atomicAdd(&ctl->contributions, static_cast<unsigned long long>(contributed));
+        atomicMax(&ctl->maxDepth, deepest);
+    }
+}
+
+static bool queuedVariant() {
+    if (const char *env = std::getenv("CORNELIS_PERSISTENT_QUEUE"))
+        return std::atoi(env) != 0;
+    return true;
+}
+
+template <bool kGrid>
+static cudaError_t configureOne(LaunchShape &shape, int &grid) {
     cudaError_t e;
-    if (shape.sceneSmemBytes > 48 * 1024)
-        if ((e = cudaFuncSetAttribute(k_persistent<kGrid>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(shape.sceneSmemBytes))) != cudaSuccess)
+    // the queued variant appends one queue per warp to the staged scene tables; scenes whose tables leave no room for
+    // the queues (close to the 227 KB carve-out) keep the lane-refill variant
+    size_t const queueOffset = (shape.sceneSmemBytes + 15u) & ~static_cast<size_t>(15u);
+    size_t const queuedBytes = queueOffset + kWarpsPerBlock * kQueueBytesPerWarp;
+    shape.persistentQueued = queuedVariant() && queuedBytes <= shape.smemOptin;
+    shape.persistentSmemBytes = shape.persistentQueued ? queuedBytes : shape.sceneSmemBytes;
+    shape.persistentQueueOffset = static_cast<uint32_t>(queueOffset);
+    auto kernel = shape.persistentQueued ? reinterpret_cast<const void *>(k_persistent_queued<kGrid>)
+                                         : reinterpret_cast<const void *>(k_persistent<kGrid>);
+    if (shape.persistentSmemBytes > 48 * 1024)
+        if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(shape.persistentSmemBytes))) != cudaSuccess)
             return e;
+    if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
+        return e;
     int blocks = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_persistent<kGrid>, kBlockThreads,
-                                                           shape.sceneSmemBytes)) != cudaSuccess)
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, kBlockThreads,
+                                                           shape.persistentSmemBytes)) != cudaSuccess)
         return e;
     if (const char *env = std::getenv("CORNELIS_PERSISTENT_BLOCKS_PER_SM"))
         if (std::atoi(env) > 0)
@@ -196,12 +395,19 @@ cudaError_t configurePersistent(LaunchShape &shape, bool gridScene, int &grid) {
 void launchPersistent(cudaStream_t s, const LaunchShape &shape, int grid, const RenderConfig &cfg, const SceneView &scene,
                       unsigned long long *cursor, unsigned long long limit, float4 *accum, float4 *accum2,
                       bool dropNonFinite, Control *ctl) {
-    if (scene.grid.enabled)
-        k_persistent<true><<<grid, kBlockThreads, shape.sceneSmemBytes, s>>>(cfg, scene, cursor, limit, accum, accum2,
-                                                                             dropNonFinite, ctl);
-    else
-        k_persistent<false><<<grid, kBlockThreads, shape.sceneSmemBytes, s>>>(cfg, scene, cursor, limit, accum, accum2,
-                                                                              dropNonFinite, ctl);
+    size_t const smem = shape.persistentSmemBytes;
+    if (shape.persistentQueued) {
+        if (scene.grid.enabled)
+            k_persistent_queued<true><<<grid, kBlockThreads, smem, s>>>(cfg, scene, cursor, limit, accum, accum2,
+                                                                        dropNonFinite, ctl, shape.persistentQueueOffset);
+        else
+            k_persistent_queued<false><<<grid, kBlockThreads, smem, s>>>(cfg, scene, cursor, limit, accum, accum2,
+                                                                         dropNonFinite, ctl, shape.persistentQueueOffset);
+    } else if (scene.grid.enabled) {
+        k_persistent<true><<<grid, kBlockThreads, smem, s>>>(cfg, scene, cursor, limit, accum, accum2, dropNonFinite, ctl);
+    } else {
+        k_persistent<false><<<grid, kBlockThreads, smem, s>>>(cfg, scene, cursor, limit, accum, accum2, dropNonFinite, ctl);
+    }
 }
 
 } // namespace cornelis_b200

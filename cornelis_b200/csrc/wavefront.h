@@ -17,6 +17,11 @@ struct LaunchShape {
     int gridRaygen = 592, gridIntersect = 592, gridIntersectGrid = 592, gridWalk = 592, gridShade = 592, gridAccumulate = 592;
     bool walkPull = true;     // grid scenes: k_walk (warps pull rays) + k_compact_hits instead of one ray per thread
     size_t sceneSmemBytes = 0;
+    size_t smemOptin = 227 * 1024;        // largest dynamic shared memory a CTA may opt in to; queried at scene creation
+    // persistent pipeline (persistent.cu): which variant runs, its dynamic shared memory and where its queues start
+    bool persistentQueued = true;
+    size_t persistentSmemBytes = 0;
+    uint32_t persistentQueueOffset = 0;
 };
 
 // Opts the kernels in to the scene's shared-memory size and fills the persistent grid sizes.
