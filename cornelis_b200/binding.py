@@ -17,6 +17,7 @@ LIB_PATH = Path(os.environ.get("CORNELIS_CUDA_LIB") or Path(__file__).resolve().
 # every symbol include/cornelis_cuda.h declares
 EXPORTS = [
     "cornelis_cuda_abi_version", "cornelis_cuda_last_error", "cornelis_cuda_device_count",
+    "cornelis_cuda_trim_memory",
     "cornelis_cuda_scene_create", "cornelis_cuda_scene_destroy", "cornelis_cuda_scene_set_stream",
     "cornelis_cuda_scene_set_acceleration", "cornelis_cuda_scene_acceleration", "cornelis_cuda_render_accumulate",
     "cornelis_cuda_framebuffer_device", "cornelis_cuda_reduce_framebuffers", "cornelis_cuda_resolve", "cornelis_cuda_resolve_device",
@@ -119,6 +120,11 @@ def lib():
 def _check(rc):
     if rc != 0:
         raise CornelisError(rc, lib().cornelis_cuda_last_error().decode())
+
+
+def trim_memory() -> None:
+    """Returns the device memory cached from destroyed handles to the driver."""
+    _check(lib().cornelis_cuda_trim_memory())
 
 
 def device_count() -> int:

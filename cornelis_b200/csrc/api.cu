@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -36,6 +38,95 @@ int fail(cornelis_status code, const std::string &message) {
                         std::string(#expr) + ": " + cudaGetErrorString(e_));                                          \
     } while (0)
 
+// Device-memory cache.  A render service creates and destroys scene handles all the time (bench.py's end-to-end leg
+// does so every step), and cudaFree / cudaMalloc of the framebuffer-sized blocks cost up to 400 ms per call on the
+// B200 boxes (measured: profiles/r2_queue/e2e_breakdown.txt) — a third of a 1080p, 4096-spp render.  Blocks released
+// by a handle are therefore kept per device, keyed by size, and handed to the next request of a similar size;
+// cornelis_cuda_trim_memory() returns them to the driver.  At most kCacheLimitBytes stay cached per process.
+class DeviceCache {
+  public:
+    cudaError_t take(void **ptr, size_t bytes) {
+        int device = 0;
+        cudaGetDevice(&device);
+        size_t const rounded = roundUp(bytes);
+        {
+            std::lock_guard<std::mutex> lock(mutex_);
+            auto &blocks = free_[device];
+            auto it = blocks.lower_bound(rounded);
+            if (it != blocks.end() && it->first <= rounded + rounded / 4) { // at most 25 % larger than asked for
+                *ptr = it->second;
+                cached_ -= it->first;
+                sizes_[*ptr] = it->first;
+                blocks.erase(it);
+                return cudaSuccess;
+            }
+        }
+        cudaError_t e = cudaMalloc(ptr, rounded);
+        if (e == cudaErrorMemoryAllocation) { // give the cached blocks back and try once more
+            cudaGetLastError();
+            trim();
+            e = cudaMalloc(ptr, rounded);
+        }
+        if (e == cudaSuccess) {
+            std::lock_guard<std::mutex> lock(mutex_);
+            sizes_[*ptr] = rounded;
+        }
+        return e;
+    }
+    // The caller has made sure no work that uses the block is still in flight.
+    void give(void *ptr) {
+        int device = 0;
+        cudaGetDevice(&device);
+        size_t bytes = 0;
+        {
+            std::lock_guard<std::mutex> lock(mutex_);
+            auto it = sizes_.find(ptr);
+            if (it != sizes_.end()) {
+                bytes = it->second;
+                sizes_.erase(it);
+                if (cached_ + bytes <= kCacheLimitBytes) {
+                    free_[device].emplace(bytes, ptr);
+                    cached_ += bytes;
+                    return;
+                }
+            }
+        }
+        cudaFree(ptr);
+    }
+    void trim() {
+        std::map<int, std::multimap<size_t, void *>> blocks;
+        {
+            std::lock_guard<std::mutex> lock(mutex_);
+            blocks.swap(free_);
+            cached_ = 0;
+        }
+        int current = 0;
+        cudaGetDevice(&current);
+        for (auto &perDevice : blocks) {
+            cudaSetDevice(perDevice.first);
+            for (auto &b : perDevice.second)
+                cudaFree(b.second);
+        }
+        cudaSetDevice(current);
+    }
+
+  private:
+    static size_t roundUp(size_t bytes) { // 512-byte granules below 1 MiB, 1 MiB granules above
+        size_t const g = bytes < (1u << 20) ? 512u : (1u << 20);
+        return (std::max<size_t>(bytes, 1) + g - 1) / g * g;
+    }
+    static constexpr size_t kCacheLimitBytes = size_t(8) << 30;
+    std::mutex mutex_;
+    std::map<int, std::multimap<size_t, void *>> free_; // device -> size -> block
+    std::map<void *, size_t> sizes_;                    // blocks handed out
+    size_t cached_ = 0;
+};
+
+DeviceCache &deviceCache() {
+    static DeviceCache *cache = new DeviceCache; // never destroyed: handles may outlive static destruction order
+    return *cache;
+}
+
 template <typename T>
 struct DeviceBuffer {
     T *ptr = nullptr;
@@ -44,7 +135,7 @@ struct DeviceBuffer {
         if (n <= count)
             return cudaSuccess;
         release();
-        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ptr), n * sizeof(T));
+        cudaError_t e = deviceCache().take(reinterpret_cast<void **>(&ptr), n * sizeof(T));
         if (e == cudaSuccess)
             count = n;
         else
@@ -52,8 +143,10 @@ struct DeviceBuffer {
         return e;
     }
     void release() {
-        if (ptr)
-            cudaFree(ptr);
+        if (ptr) {
+            cudaDeviceSynchronize(); // what cudaFree did implicitly: nothing in flight may still use the block
+            deviceCache().give(ptr);
+        }
         ptr = nullptr;
         count = 0;
     }
@@ -268,6 +361,11 @@ int applyAcceleration(cornelis_cuda_scene *s, int mode) {
 extern "C" {
 
 int cornelis_cuda_abi_version(void) { return CORNELIS_CUDA_ABI_VERSION; }
+
+int cornelis_cuda_trim_memory(void) {
+    deviceCache().trim();
+    return CORNELIS_OK;
+}
 
 const char *cornelis_cuda_last_error(void) { return g_lastError.c_str(); }
 

@@ -25,12 +25,23 @@ namespace cornelis_b200 {
 
 constexpr unsigned long long kClaim = 1024; // camera paths a warp claims per atomic
 
+// CTA shape of the persistent kernels, measured on B200 with the queued variant (Cornell 1080p, Msamples/s):
+//   256 threads x 4 CTAs/SM (64 registers, 32 warps/SM) 6332     256 x 3 (80 registers, 24 warps) 7103
+//   256 x 2 (128 registers, 16 warps) 7260    128 x 7 (72, 28 warps) 7036    128 x 6 (80, 24 warps) 7396
+//   128 x 5 (96 registers, 20 warps/SM) 7509
+// The loop body is ~28 KB of hot code against a 32 KB instruction cache, and at 64 registers ptxas rematerialises
+// and spills: fewer, fatter warps issue fewer instructions and fetch from fewer places at once.
 #ifndef CORNELIS_PERSISTENT_MIN_BLOCKS
-#define CORNELIS_PERSISTENT_MIN_BLOCKS 4
+#define CORNELIS_PERSISTENT_MIN_BLOCKS 5
 #endif
+#ifndef CORNELIS_PERSISTENT_THREADS
+#define CORNELIS_PERSISTENT_THREADS 128
+#endif
+constexpr int kPersistentThreads = CORNELIS_PERSISTENT_THREADS; // CTA size of the persistent kernels
+constexpr int kPersistentWarps = kPersistentThreads / 32;
 
 template <bool kGrid>
-__global__ void __launch_bounds__(kBlockThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
+__global__ void __launch_bounds__(kPersistentThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
     k_persistent(RenderConfig cfg, SceneView scene, unsigned long long *__restrict__ cursor, unsigned long long limit,
                  float4 *__restrict__ accum, float4 *__restrict__ accum2, bool dropNonFinite, Control *__restrict__ ctl) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -190,7 +201,7 @@ constexpr uint32_t kQueueChunks = 5;
 constexpr size_t kQueueBytesPerWarp = kQueueSlots * kQueueChunks * sizeof(float4);
 
 template <bool kGrid>
-__global__ void __launch_bounds__(kBlockThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
+__global__ void __launch_bounds__(kPersistentThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
     k_persistent_queued(RenderConfig cfg, SceneView scene, unsigned long long *__restrict__ cursor,
                         unsigned long long limit, float4 *__restrict__ accum, float4 *__restrict__ accum2,
                         bool dropNonFinite, Control *__restrict__ ctl, uint32_t queueOffset) {
@@ -364,7 +375,7 @@ static cudaError_t configureOne(LaunchShape &shape, int &grid) {
     // the queued variant appends one queue per warp to the staged scene tables; scenes whose tables leave no room for
     // the queues (close to the 227 KB carve-out) keep the lane-refill variant
     size_t const queueOffset = (shape.sceneSmemBytes + 15u) & ~static_cast<size_t>(15u);
-    size_t const queuedBytes = queueOffset + kWarpsPerBlock * kQueueBytesPerWarp;
+    size_t const queuedBytes = queueOffset + kPersistentWarps * kQueueBytesPerWarp;
     shape.persistentQueued = queuedVariant() && queuedBytes <= shape.smemOptin;
     shape.persistentSmemBytes = shape.persistentQueued ? queuedBytes : shape.sceneSmemBytes;
     shape.persistentQueueOffset = static_cast<uint32_t>(queueOffset);
@@ -378,7 +389,7 @@ static cudaError_t configureOne(LaunchShape &shape, int &grid) {
                                   cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
         return e;
     int blocks = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, kBlockThreads,
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, kPersistentThreads,
                                                            shape.persistentSmemBytes)) != cudaSuccess)
         return e;
     if (const char *env = std::getenv("CORNELIS_PERSISTENT_BLOCKS_PER_SM"))
@@ -398,15 +409,15 @@ void launchPersistent(cudaStream_t s, const LaunchShape &shape, int grid, const 
     size_t const smem = shape.persistentSmemBytes;
     if (shape.persistentQueued) {
         if (scene.grid.enabled)
-            k_persistent_queued<true><<<grid, kBlockThreads, smem, s>>>(cfg, scene, cursor, limit, accum, accum2,
+            k_persistent_queued<true><<<grid, kPersistentThreads, smem, s>>>(cfg, scene, cursor, limit, accum, accum2,
                                                                         dropNonFinite, ctl, shape.persistentQueueOffset);
         else
-            k_persistent_queued<false><<<grid, kBlockThreads, smem, s>>>(cfg, scene, cursor, limit, accum, accum2,
+            k_persistent_queued<false><<<grid, kPersistentThreads, smem, s>>>(cfg, scene, cursor, limit, accum, accum2,
                                                                          dropNonFinite, ctl, shape.persistentQueueOffset);
     } else if (scene.grid.enabled) {
-        k_persistent<true><<<grid, kBlockThreads, smem, s>>>(cfg, scene, cursor, limit, accum, accum2, dropNonFinite, ctl);
+        k_persistent<true><<<grid, kPersistentThreads, smem, s>>>(cfg, scene, cursor, limit, accum, accum2, dropNonFinite, ctl);
     } else {
-        k_persistent<false><<<grid, kBlockThreads, smem, s>>>(cfg, scene, cursor, limit, accum, accum2, dropNonFinite, ctl);
+        k_persistent<false><<<grid, kPersistentThreads, smem, s>>>(cfg, scene, cursor, limit, accum, accum2, dropNonFinite, ctl);
     }
 }
 

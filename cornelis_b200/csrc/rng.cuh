@@ -16,6 +16,13 @@
 
 namespace cornelis_b200 {
 
+#ifndef CORNELIS_PHILOX_UNROLL
+#define CORNELIS_PHILOX_UNROLL 10 // rounds unrolled per loop trip (10 = straight-line code)
+#endif
+#define CB_PHILOX_PRAGMA(x) _Pragma(#x)
+#define CB_PHILOX_UNROLL_N(n) CB_PHILOX_PRAGMA(unroll n)
+#define CB_PHILOX_UNROLL CB_PHILOX_UNROLL_N(CORNELIS_PHILOX_UNROLL)
+
 struct Philox4 {
     uint32_t v[4];
 };
@@ -57,7 +64,7 @@ inline PhiloxKeys makePhiloxKeys(uint32_t key0, uint32_t key1) {
 __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                           const PhiloxKeys &keys) {
     constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
-#pragma unroll
+    CB_PHILOX_UNROLL
     for (int round = 0; round < 10; round++) {
         unsigned long long p0 = static_cast<unsigned long long>(M0) * c0;
         unsigned long long p1 = static_cast<unsigned long long>(M1) * c2;

@@ -125,6 +125,10 @@ typedef int (*cornelis_progress_fn)(void *user, uint64_t samples_done, uint64_t 
 int cornelis_cuda_abi_version(void);
 const char *cornelis_cuda_last_error(void);
 int cornelis_cuda_device_count(int *count);
+/* Device memory released by destroyed (or resized) handles is kept for the next handle of this process instead of
+ * going back to the driver (the reference allocates its FrameBuffer per render, Render.cpp:307; on the GPU that
+ * allocation is the expensive part of a short render).  This call returns the cached blocks to the driver. */
+int cornelis_cuda_trim_memory(void);
 
 /* ---- scene: replaces SceneData construction (Scene.cpp:40-53) + upload ------------------------------------------ */
 

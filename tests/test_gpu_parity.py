@@ -401,6 +401,40 @@ def test_render_end_to_end_and_display_transform(binding, oracle):
     assert img[:24].mean() > 0
 
 
+def test_handle_churn_reuses_device_memory(binding):
+    """Handles created and destroyed in a loop (bench.py's end-to-end leg) take their buffers from the library's
+    device-memory cache: a block that held another handle's framebuffer, or a smaller / larger frame, must not leak
+    into the image.  cornelis_cuda_trim_memory hands the cache back and the next handle still works."""
+    images = []
+    for k, (w, h) in enumerate([(96, 64), (96, 64), (64, 32), (128, 96), (96, 64)]):
+        sc = binding.Scene(scenes.cornell_box())
+        img, st = sc.render(w, h, 16)
+        assert st["pixel_samples"] == w * h * 16 and np.isfinite(img).all()
+        if (w, h) == (96, 64):
+            images.append(img.copy())
+        sc.close()
+        if k == 2:
+            binding.trim_memory()
+    for img in images[1:]:
+        assert np.allclose(images[0], img, rtol=1e-5, atol=1e-6)  # same paths; atomics reorder the fp32 sums
+
+
+def test_persistent_batches_of_any_size(binding):
+    """The persistent kernel parks Russian-roulette survivors per warp and scatters them 32 at a time; frames with
+    fewer pixels than a warp, sample ranges that end inside a warp's claim, and the final partial batches must
+    account for every path exactly once (same counters as the wavefront pipeline, which has no such batching)."""
+    sc = binding.Scene(scenes.cornell_box())
+    for (w, h, spp) in [(5, 3, 7), (1, 1, 1), (33, 1, 3), (64, 64, 5), (257, 3, 2)]:
+        st_w = sc.render_accumulate(w, h, spp, pipeline=1)
+        img_w = sc.resolve(spp).copy()
+        st_p = sc.render_accumulate(w, h, spp, pipeline=2)
+        img_p = sc.resolve(spp)
+        for key in ("pixel_samples", "rays", "shaded_hits", "max_depth", "contributions"):
+            assert st_w[key] == st_p[key], (w, h, spp, key, st_w[key], st_p[key])
+        assert st_p["pixel_samples"] == w * h * spp
+        assert np.allclose(img_w, img_p, rtol=1e-5, atol=1e-6)
+
+
 def test_depth_cap_and_argument_errors(binding):
     sc = binding.Scene(scenes.cornell_box())
     st = sc.render_accumulate(64, 64, 8, max_depth=2)
