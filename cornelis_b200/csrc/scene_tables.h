@@ -112,6 +112,9 @@ inline bool buildGrid(const cornelis_sphere_desc *spheres, size_t n, const doubl
     double ext[3], volume = 1;
     for (int a = 0; a < 3; a++) {
         gmin[a] -= delta, gmax[a] += delta;
+        if (!(std::fabs(gmin[a]) <= 0x1.0p30 && std::fabs(gmax[a]) <= 0x1.0p30 && std::fabs(rmin[a]) <= 0x1.0p30 &&
+              std::fabs(rmax[a]) <= 0x1.0p30))
+            return false; // outside the range the hoisted sphere test is exact for (geometry.cuh)
         ext[a] = gmax[a] - gmin[a];
         if (!(ext[a] > 0) || !std::isfinite(ext[a]))
             return false;

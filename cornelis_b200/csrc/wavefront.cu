@@ -113,8 +113,18 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_INTERSECT_MIN_BLOCKS) 
 // idle — because setting up a walk (plane tests, clipping, DDA) is itself ~150 instructions.  Only the hit records are
 // written here; k_compact_hits builds the queues (compaction #1) in a streaming pass.
 constexpr unsigned kWalkClaim = 256;  // rays a warp claims per atomic
-constexpr unsigned kWalkRefill = 8;   // idle lanes that trigger a refill
-constexpr unsigned kWalkTestCost = 11, kWalkAdvanceCost = 5; // relative instruction counts of the two kinds of step
+#ifndef CORNELIS_WALK_REFILL
+#define CORNELIS_WALK_REFILL 8
+#endif
+#ifndef CORNELIS_WALK_TEST_COST
+#define CORNELIS_WALK_TEST_COST 11
+#endif
+#ifndef CORNELIS_WALK_ADVANCE_COST
+#define CORNELIS_WALK_ADVANCE_COST 5
+#endif
+constexpr unsigned kWalkRefill = CORNELIS_WALK_REFILL; // idle lanes that trigger a refill
+// relative instruction counts of the two kinds of step
+constexpr unsigned kWalkTestCost = CORNELIS_WALK_TEST_COST, kWalkAdvanceCost = CORNELIS_WALK_ADVANCE_COST;
 
 #ifndef CORNELIS_WALK_MIN_BLOCKS
 #define CORNELIS_WALK_MIN_BLOCKS 4
@@ -175,7 +185,7 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_WALK_MIN_BLOCKS)
         // A burst of rounds.  A walking lane wants one of two things: to TEST the next sphere of its cell (~55
         // instructions) or, when the cell has none left — empty cells are the common case — to ADVANCE to the next
         // cell (~25).  Executing both per round (one mixed step per lane) left 11.9 of 32 lanes active per instruction
-        // (profiles/r2_walk); instead every round runs only the kind of step that moves more lanes per instruction
+        // (profiles/r1_queue: 18.1 lanes after the change); instead every round runs only the kind of step that moves more lanes per instruction
         // issued, and the others wait for a round of their kind.  The burst stops early when enough lanes have finished
         // to make a refill worthwhile.
 #pragma unroll 1
