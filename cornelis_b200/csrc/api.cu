@@ -428,9 +428,11 @@ int cornelis_cuda_scene_create(int device, const cornelis_camera_desc *camera, c
     // SphereData / PlaneData / materials (Scene.cpp:5-53) flattened to the device tables.
     std::vector<DevSphere> hs(n_spheres);
     std::vector<uint32_t> hsm(n_spheres);
+    bool radiiSafe = true; // see geometry.cuh scanSpheres
     for (size_t i = 0; i < n_spheres; i++) {
         hs[i] = DevSphere{spheres[i].center[0], spheres[i].center[1], spheres[i].center[2],
                           spheres[i].radius * spheres[i].radius};
+        radiiSafe = radiiSafe && hs[i].r2 >= 0x1.0p-50f;
         hsm[i] = spheres[i].material >= 0 ? static_cast<uint32_t>(spheres[i].material) : 0u; // value_or(0)
     }
     std::vector<DevPlane> hp(n_planes);
@@ -477,6 +479,7 @@ int cornelis_cuda_scene_create(int device, const cornelis_camera_desc *camera, c
     s->view.nSpheres = static_cast<uint32_t>(n_spheres);
     s->view.nPlanes = static_cast<uint32_t>(n_planes);
     s->view.nMaterials = static_cast<uint32_t>(n_materials);
+    s->view.radiiSafe = radiiSafe ? 1u : 0u;
     s->view.planeOrder = s->planeOrder.ptr;
     s->view.planeEnd[0] = classEnd[0], s->view.planeEnd[1] = classEnd[1], s->view.planeEnd[2] = classEnd[2];
     s->view.camera = makeCamera(*camera);

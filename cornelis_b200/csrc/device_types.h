@@ -65,7 +65,8 @@ struct SceneView {
     const uint32_t *sphereMaterial;
     const DevPlane *planes;
     const DevMaterial *materials;
-    uint32_t nSpheres, nPlanes, nMaterials, pad;
+    uint32_t nSpheres, nPlanes, nMaterials;
+    uint32_t radiiSafe; // every r^2 >= 2^-50: C - r^2 is then 0 or at least 2^-75 in magnitude (geometry.cuh scanSpheres)
     // Plane indices sorted by axis class (then by index): [0, planeEnd[0]) have normals along x, [planeEnd[0],
     // planeEnd[1]) along y, [planeEnd[1], planeEnd[2]) along z, the rest are general.  closestHit runs one tight loop
     // per class instead of dispatching on the class of every plane.

@@ -77,13 +77,13 @@ __device__ __forceinline__ SharedScene stageScene(const SceneView &scene, unsign
 
 // The intersect stage for either scene representation.  kGrid is a template parameter of the kernels (the host picks
 // the instantiation from SceneView::grid.enabled) so the few-primitive kernels keep their register budget.
-template <bool kGrid>
+template <bool kGrid, int kSphereUnroll = 1>
 __device__ __forceinline__ void closestHitScene(bool live, V3 o, V3 d, const SharedScene &sh, const SceneView &scene,
                                                 float &tBest, int32_t &primBest) {
     if (kGrid)
         closestHitGrid(live, o, d, scene, sh.planes, tBest, primBest);
     else
-        closestHit(live, o, d, sh, scene, tBest, primBest);
+        closestHit<kSphereUnroll>(live, o, d, sh, scene, tBest, primBest);
 }
 
 // ------------------------------------------------------------------------------------------------ compaction --

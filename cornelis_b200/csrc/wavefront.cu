@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_intersect_batch(SceneView sce
         }
         float t = INFINITY;
         int32_t prim = -1;
-        closestHitScene<kGrid>(valid, V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, sh, scene, t, prim);
+        closestHitScene<kGrid, 4>(valid, V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, sh, scene, t, prim);
         if (valid)
             hits[i] = HitRecord{t, prim};
     }

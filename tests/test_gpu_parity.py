@@ -194,6 +194,53 @@ def test_rays_starting_on_planes_keep_the_sign_of_zero(binding, oracle):
     assert zero.sum() > n // 4 and np.signbit(b["t"][zero]).any() and (~np.signbit(b["t"][zero])).any()
 
 
+def test_rays_on_and_tangent_to_spheres(binding, oracle):
+    """Zero numerators of the sphere test (Geometry.cpp:77-84): an origin exactly on a sphere (C == r^2), a direction
+    perpendicular to the centre offset (B == 0), both at once (t = 0 from a zero discriminant) and exact tangents.
+    The fast path returns zeros whose sign may differ from the operators' inside the test, which must never reach t;
+    spheres with tiny radii (r^2 < 2^-50) switch the scene to the operator scan.  All against the oracle, bit for
+    bit, through the exhaustive scan and through the grid."""
+    flat = scenes.microbench_scene(64)
+    sph = flat["spheres"].copy()
+    sph[0] = [0, 0, 0, 1]            # unit sphere at the origin
+    sph[1] = [8, -4, 2, 0.5]         # power-of-two data: exact zeros are reachable
+    sph[2] = [-16, 32, 64, 4]
+    flat["spheres"] = sph.astype(np.float32)
+    rng = np.random.default_rng(11)
+    n = 60000
+    o = np.zeros((n, 3), np.float32)
+    d = unit(rng, n)
+    k = np.arange(n) % 12
+    which = sph[(np.arange(n) // 12) % 3]
+    c, r = which[:, :3], which[:, 3:4]
+    axis = np.eye(3, dtype=np.float32)[(np.arange(n) // 36) % 3]
+    other = np.roll(axis, 1, axis=1)
+    sign = np.where((np.arange(n) // 108) % 2 == 0, np.float32(1), np.float32(-1))[:, None]
+    o[:] = c + sign * r * axis                         # exactly on the surface: C == r^2
+    d[k == 0] = (-sign * axis)[k == 0]                 # straight through the centre
+    d[k == 1] = (sign * axis)[k == 1]                  # straight away from it
+    d[k == 2] = other[k == 2]                          # tangent from the surface: B == 0 and C == r^2
+    d[k == 3] = (-other)[k == 3]
+    o[k == 4] = (c + np.float32(0.5) * r * axis)[k == 4]   # inside, perpendicular: B == 0
+    d[k == 4] = other[k == 4]
+    o[k == 5] = (c + sign * r * axis - np.float32(4) * other)[k == 5]   # exact tangent from outside
+    d[k == 5] = other[k == 5]
+    d[k == 6] = (other * np.float32(3))[k == 6]        # non-unit directions (test_Geometry.cpp:46)
+    d[k == 7] = (-sign * axis * np.float32(0.25))[k == 7]
+    # k >= 8: random directions from the surface
+    for tiny in (False, True):
+        if tiny:
+            flat["spheres"][3] = [100, 100, 100, 1e-9]   # r^2 = 1e-18 < 2^-50
+        sc, osc = binding.Scene(flat), oracle.scene(flat)
+        ref = osc.intersect(o, d)
+        for accel in (binding.ACCEL_NONE, binding.ACCEL_GRID):
+            sc.set_acceleration(accel)
+            got = sc.intersect(o, d, surface=False)
+            assert np.array_equal(got["prim"], ref["prim"]), (tiny, accel)
+            assert bit_equal(got["t"], ref["t"]), (tiny, accel)
+    assert (ref["t"] == 0).sum() > n // 8 and (ref["prim"] < 3).sum() > n // 4
+
+
 # ---------------------------------------------------------------------------------------------------- materials --
 
 def _bsdf_inputs(rng, n, n_mat):
