@@ -404,6 +404,9 @@ __global__ void __launch_bounds__(kBlockThreads) k_pixel_rays(DevCamera cam, uin
 
 // The intersect stage on a plain float4 ray batch — the same closestHit as k_intersect without the queues.
 // Used by cornelis_cuda_intersect(_device): parity tests and the intersection microbench (config 3).
+#ifndef CORNELIS_BATCH_SPHERE_GROUP
+#define CORNELIS_BATCH_SPHERE_GROUP 8 // spheres per discriminant vote (geometry.cuh scanSpheres)
+#endif
 template <bool kGrid>
 __global__ void __launch_bounds__(kBlockThreads) k_intersect_batch(SceneView scene, size_t n,
                                                                    const float4 *__restrict__ org,
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_intersect_batch(SceneView sce
         }
         float t = INFINITY;
         int32_t prim = -1;
-        closestHitScene<kGrid, 4>(valid, V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, sh, scene, t, prim);
+        closestHitScene<kGrid, CORNELIS_BATCH_SPHERE_GROUP>(valid, V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, sh, scene, t, prim);
         if (valid)
             hits[i] = HitRecord{t, prim};
     }
