@@ -37,12 +37,14 @@ FLOP_PER_RAY_CORNELL = 4 * 26 + 5 * 35        # 279: 4 sphere tests x 26 flop + 
 FLOP_PER_SURVIVING_BOUNCE = 250
 FLOP_PER_KILLED_HIT = 12
 # bytes per item of the wavefront layout (DESIGN.md "Data layout"): see roofline() below
-# DRAM traffic of k_persistent from the committed ncu capture (profiles/r1_diet/
-# ncu_full_summary_k_persistent_cornell_512spp.txt): dram__bytes_read.sum + dram__bytes_write.sum = 32.58 MB + 0.33 MB
-# for one launch of 1920x1080 x 512 spp.  The only global traffic is framebuffer atomics over a 33 MB image that
-# lives in the 126 MB L2, so DRAM sees little more than one read of the image per launch.
-NCU_PERSISTENT_DRAM_BYTES = 32.576768e6 + 0.331008e6
-NCU_PERSISTENT_PIXEL_SAMPLES = 1920 * 1080 * 512
+# DRAM traffic of the persistent kernel from the committed ncu capture (profiles/r1_queue/
+# ncu_full_summary_k_persistent_queued_cornell_512spp.txt): dram__bytes_read.sum + dram__bytes_write.sum = 32.90 MB +
+# 0.12 MB for one launch of 1920x1080 x 512 spp.  The only global traffic is framebuffer atomics over a 33 MB image
+# that lives in the 126 MB L2, so DRAM sees one read of the image per launch whatever the sample count (a 64-spp
+# launch: 31.65 MB + 0.02 MB): the figure is reported as captured, not scaled.
+NCU_PERSISTENT_DRAM_BYTES = 32.897280e6 + 0.121856e6
+NCU_PERSISTENT_ISSUE = {"busy_pct": 84.6, "warp_instructions_per_ray": 38.0, "lanes_per_instruction": 29.0,
+                        "no_instruction_stall_per_issue": 0.69, "registers": 72, "ctas_per_sm": "7 x 128 threads"}
 
 
 def parse_args():
@@ -219,7 +221,7 @@ def roofline(stats_list, hbm_peak, hbm_source, persistent):
     extra = {}
     if persistent:
         launches = max(1, tot["kernel_launches"])
-        name = "k_persistent"
+        name = "k_persistent_queued"
         ms = sum(s["gpu_ms"] for s in stats_list) / launches
         flop = (FLOP_PER_RAY_CORNELL * tot["rays"] + FLOP_PER_SURVIVING_BOUNCE * surviving +
                 FLOP_PER_KILLED_HIT * killed) / launches
@@ -227,13 +229,14 @@ def roofline(stats_list, hbm_peak, hbm_source, persistent):
         # (16 B read + 16 B written) of paths that end with non-zero radiance
         nbytes = 32.0 * tot["contributions"] / launches
         extra["rays_per_launch"] = tot["rays"] / launches
-        extra["traffic"] = NCU_PERSISTENT_DRAM_BYTES * (tot["pixel_samples"] / launches) / NCU_PERSISTENT_PIXEL_SAMPLES
+        extra["traffic"] = NCU_PERSISTENT_DRAM_BYTES
         extra["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of a "
-                                   "512-spp launch (profiles/r1_diet), scaled by pixel-samples per launch; below the "
-                                   "algorithmic bytes because the 33 MB framebuffer stays in L2")
-        extra["issue_slots"] = {"busy_pct": 86.6, "warp_instructions_per_ray": 49.4, "lanes_per_instruction": 23.2,
-                                "source": "same capture: smsp__issue_active, smsp__inst_executed.sum / rays, "
-                                          "smsp__thread_inst_executed_per_inst_executed"}
+                                   "1920x1080 x 512-spp launch of the same kernel (profiles/r1_queue); not scaled: the "
+                                   "33 MB framebuffer lives in L2 and DRAM sees one read of it per launch whatever the "
+                                   "sample count, far below the algorithmic bytes of the framebuffer atomics")
+        extra["issue_slots"] = dict(NCU_PERSISTENT_ISSUE,
+                                    source="same capture: smsp__issue_active, smsp__inst_executed.sum / rays, "
+                                           "smsp__thread_inst_executed_per_inst_executed, stall_no_instruction")
     else:
         launches = max(1, tot["iterations"])
         stage = {k: statistics.mean(s[k] for s in stats_list)
