@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_raygen(const Control *ctl, Re
 // shared memory, then compaction #1: hits are appended to the hit queue; misses end the path — if it carries
 // radiance it goes to the finished queue, otherwise it simply disappears.
 #ifndef CORNELIS_INTERSECT_MIN_BLOCKS
-#define CORNELIS_INTERSECT_MIN_BLOCKS 6
+#define CORNELIS_INTERSECT_MIN_BLOCKS 5
 #endif
 template <bool kGrid>
 __global__ void __launch_bounds__(kBlockThreads, CORNELIS_INTERSECT_MIN_BLOCKS) k_intersect(Control *ctl, SceneView scene, PathPool pool,
