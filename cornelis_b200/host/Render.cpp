@@ -6,6 +6,7 @@
 // are summed on device 0 and resolved into the RGBFrameBuffer.  No CPU rendering path exists here.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <mutex>
 #include <string>
@@ -129,6 +130,7 @@ struct ProgressRelay {
     std::vector<std::atomic<std::uint64_t>> *done;
     std::size_t device;
     std::uint64_t total;
+    std::uint64_t doneBefore; // pixel-samples of earlier slices
     std::atomic<bool> *abort;
 };
 
@@ -136,6 +138,7 @@ int relay(void *user, std::uint64_t samplesDone, std::uint64_t) {
     auto *r = static_cast<ProgressRelay *>(user);
     (*r->done)[r->device].store(samplesDone);
     RenderProgress p;
+    p.samplesDone = r->doneBefore;
     for (auto const &d : *r->done)
         p.samplesDone += d.load();
     p.samplesTotal = r->total;
@@ -153,82 +156,151 @@ void RenderSession::render(ProgressCallback onProgress) {
         return;
     }
     std::size_t const n = s.devices.size();
-    std::uint64_t const total = static_cast<std::uint64_t>(o.width) * static_cast<std::uint64_t>(o.height) *
-                                static_cast<std::uint64_t>(o.samplesAA);
+    std::uint64_t const npixels = static_cast<std::uint64_t>(o.width) * static_cast<std::uint64_t>(o.height);
+    std::uint64_t const total = npixels * static_cast<std::uint64_t>(o.samplesAA);
+    bool const progressive = o.progressive || o.timeBudgetSeconds > 0.0;
     std::vector<std::atomic<std::uint64_t>> done(n);
-    for (auto &d : done)
-        d.store(0);
     std::atomic<bool> abort{false};
     std::vector<int> rc(n, 0);
     std::vector<std::string> errors(n);
     std::vector<cornelis_render_stats> stats(n);
+    s.stats = RenderStatistics{};
+    std::uint64_t doneBefore = 0; // pixel-samples of the slices already finished
 
-    auto work = [&](std::size_t dev) {
-        // contiguous sample range of this device; the counter-based RNG makes the union identical for any count
-        std::int32_t const first = static_cast<std::int32_t>(static_cast<std::int64_t>(o.samplesAA) * static_cast<std::int64_t>(dev) / static_cast<std::int64_t>(n));
-        std::int32_t const last = static_cast<std::int32_t>(static_cast<std::int64_t>(o.samplesAA) * static_cast<std::int64_t>(dev + 1) / static_cast<std::int64_t>(n));
-        if (last == first) {
-            rc[dev] = -1; // nothing to do on this device
-            return;
+    // Renders the global sample indices [first, first + count) of every pixel, split over the devices as contiguous
+    // sub-ranges (the counter-based RNG makes the union identical for any device count), and leaves the sum of ALL
+    // samples rendered so far in device 0's accumulators: device 0 keeps its accumulators from slice to slice, the
+    // other devices start every slice from zero and are added to it.  Returns false if the render was aborted.
+    auto renderRange = [&](std::int32_t first, std::int32_t count, bool keep) -> bool {
+        for (auto &d : done)
+            d.store(0);
+        auto work = [&](std::size_t dev) {
+            // device 0 takes the LAST sub-range, which is never empty: the sum of all devices lives on device 0
+            std::int64_t const part = static_cast<std::int64_t>(n - 1 - dev), parts = static_cast<std::int64_t>(n);
+            std::int32_t const lo = first + static_cast<std::int32_t>(static_cast<std::int64_t>(count) * part / parts);
+            std::int32_t const hi = first + static_cast<std::int32_t>(static_cast<std::int64_t>(count) * (part + 1) / parts);
+            stats[dev] = cornelis_render_stats{};
+            if (hi == lo) {
+                rc[dev] = -1; // nothing to do on this device
+                return;
+            }
+            cornelis_render_params p{};
+            p.width = o.width;
+            p.height = o.height;
+            p.samples = o.samplesAA;
+            p.first_sample = lo;
+            p.sample_count = hi - lo;
+            p.max_depth = o.maxDepth;
+            p.seed = o.seed;
+            p.flags = (o.dropNonFinite ? CORNELIS_RENDER_DROP_NONFINITE : 0u) | (keep && dev == 0 ? CORNELIS_RENDER_KEEP : 0u);
+            p.pool_paths = o.poolPaths;
+            ProgressRelay r{&onProgress, &done, dev, total, doneBefore, &abort};
+            // a progressive render reports after every slice instead of from inside the slices
+            rc[dev] = cornelis_cuda_render_accumulate(s.devices[dev].handle, &p, progressive ? nullptr : relay, &r, &stats[dev]);
+            if (rc[dev])
+                errors[dev] = cornelis_cuda_last_error();
+        };
+        if (n == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> pool;
+            for (std::size_t dev = 0; dev < n; dev++)
+                pool.emplace_back(work, dev);
+            for (auto &t : pool)
+                t.join();
         }
-        cornelis_render_params p{};
-        p.width = o.width;
-        p.height = o.height;
-        p.samples = o.samplesAA;
-        p.first_sample = first;
-        p.sample_count = last - first;
-        p.max_depth = o.maxDepth;
-        p.seed = o.seed;
-        p.flags = o.dropNonFinite ? CORNELIS_RENDER_DROP_NONFINITE : 0u;
-        p.pool_paths = o.poolPaths;
-        ProgressRelay r{&onProgress, &done, dev, total, &abort};
-        rc[dev] = cornelis_cuda_render_accumulate(s.devices[dev].handle, &p, relay, &r, &stats[dev]);
-        if (rc[dev])
-            errors[dev] = cornelis_cuda_last_error();
+        bool aborted = false;
+        for (std::size_t dev = 0; dev < n; dev++) {
+            if (rc[dev] == CORNELIS_ERR_ABORTED)
+                aborted = true;
+            else if (rc[dev] > 0) {
+                RenderProgress failed;
+                failed.samplesDone = doneBefore;
+                failed.samplesTotal = total;
+                onProgress(failed, RenderStatus::Failed);
+                throw RenderError(rc[dev], "cornelis_cuda_render_accumulate: " + errors[dev]);
+            }
+        }
+        std::vector<cornelis_cuda_scene *> rendered;
+        double slowest = 0.0;
+        for (std::size_t dev = 0; dev < n; dev++) {
+            if (rc[dev] == -1)
+                continue;
+            rendered.push_back(s.devices[dev].handle);
+            s.stats.pixelSamples += stats[dev].pixel_samples;
+            s.stats.rays += stats[dev].rays;
+            s.stats.passes += stats[dev].iterations;
+            s.stats.kernelLaunches += stats[dev].kernel_launches;
+            s.stats.maxDepth = std::max(s.stats.maxDepth, stats[dev].max_depth);
+            slowest = std::max(slowest, 1e-3 * static_cast<double>(stats[dev].gpu_ms));
+        }
+        s.stats.gpuSeconds += slowest;
+        s.stats.slices += 1;
+        // count >= 1 puts device 0 first in `rendered`: the sum lands where the next slice keeps accumulating
+        if (rendered.size() > 1)
+            if (int e = cornelis_cuda_reduce_framebuffers(rendered.data(), static_cast<int>(rendered.size())))
+                raise(e, "cornelis_cuda_reduce_framebuffers");
+        doneBefore = s.stats.pixelSamples;
+        return !aborted;
     };
-    if (n == 1) {
-        work(0);
+    // color = sum * (1 / samples) into the RGBFrameBuffer: RGB is three packed floats, the host_rgb layout of the C-ABI
+    auto resolve = [&](std::int32_t samples) {
+        if (int e = cornelis_cuda_resolve(s.devices.front().handle, samples, reinterpret_cast<float *>(s.fb.data()), nullptr))
+            raise(e, "cornelis_cuda_resolve");
+        s.stats.samplesPerPixel = samples;
+    };
+
+    bool aborted = false;
+    if (!progressive) {
+        aborted = !renderRange(0, o.samplesAA, false);
+        resolve(o.samplesAA);
     } else {
-        std::vector<std::thread> pool;
-        for (std::size_t dev = 0; dev < n; dev++)
-            pool.emplace_back(work, dev);
-        for (auto &t : pool)
-            t.join();
+        // Slices grow geometrically (n, n, 2n, 4n, ... samples per pixel for n devices) so that the first image arrives
+        // after one sample per device and the per-slice overhead stays small; with a time budget the next slice is
+        // shrunk to what, at the rate measured so far, still ends inside the budget.
+        auto const start = std::chrono::steady_clock::now();
+        auto elapsed = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count(); };
+        std::int32_t rendered = 0;
+        std::int32_t slice = static_cast<std::int32_t>(std::min<std::size_t>(n, static_cast<std::size_t>(o.samplesAA)));
+        while (rendered < o.samplesAA) {
+            slice = std::min(slice, o.samplesAA - rendered);
+            if (o.timeBudgetSeconds > 0.0 && rendered > 0) {
+                double const perSample = elapsed() / static_cast<double>(rendered);
+                double const left = o.timeBudgetSeconds - elapsed();
+                if (left <= 0.0)
+                    break;
+                if (perSample * slice > left) { // shrink the last slice to what fits; stop when not even n samples do
+                    slice = static_cast<std::int32_t>(left / perSample);
+                    if (slice < static_cast<std::int32_t>(n))
+                        break;
+                }
+            }
+            aborted = !renderRange(rendered, slice, rendered > 0);
+            if (aborted)
+                break; // the slice is incomplete: the frame buffer keeps the last complete estimate
+            rendered += slice;
+            resolve(rendered);
+            if (rendered < o.samplesAA) {
+                RenderProgress p;
+                p.samplesDone = doneBefore;
+                p.samplesTotal = total;
+                if (onProgress(p, RenderStatus::Running) != RenderCommand::Continue) {
+                    aborted = true;
+                    break;
+                }
+            }
+            slice = rendered; // n, n, 2n, 4n, ...: every slice doubles the samples in the image
+        }
+        if (rendered == 0 && !aborted) { // a budget too small for a single slice still gets one sample per device
+            aborted = !renderRange(0, slice, false);
+            if (!aborted)
+                resolve(slice);
+        }
     }
 
     RenderProgress final;
     final.samplesTotal = total;
-    bool aborted = false;
-    for (std::size_t dev = 0; dev < n; dev++) {
-        if (rc[dev] == CORNELIS_ERR_ABORTED)
-            aborted = true;
-        else if (rc[dev] > 0) {
-            onProgress(final, RenderStatus::Failed);
-            throw RenderError(rc[dev], "cornelis_cuda_render_accumulate: " + errors[dev]);
-        }
-    }
-
-    s.stats = RenderStatistics{};
-    std::vector<cornelis_cuda_scene *> rendered;
-    for (std::size_t dev = 0; dev < n; dev++) {
-        if (rc[dev] == -1)
-            continue;
-        rendered.push_back(s.devices[dev].handle);
-        s.stats.pixelSamples += stats[dev].pixel_samples;
-        s.stats.rays += stats[dev].rays;
-        s.stats.passes += stats[dev].iterations;
-        s.stats.kernelLaunches += stats[dev].kernel_launches;
-        s.stats.maxDepth = std::max(s.stats.maxDepth, stats[dev].max_depth);
-        s.stats.gpuSeconds = std::max(s.stats.gpuSeconds, 1e-3 * static_cast<double>(stats[dev].gpu_ms));
-    }
     final.samplesDone = s.stats.pixelSamples;
-    if (rendered.size() > 1)
-        if (int e = cornelis_cuda_reduce_framebuffers(rendered.data(), static_cast<int>(rendered.size())))
-            raise(e, "cornelis_cuda_reduce_framebuffers");
-    // RGB is three packed floats, exactly the host_rgb layout of the C-ABI
-    if (int e = cornelis_cuda_resolve(rendered.front(), o.samplesAA, reinterpret_cast<float *>(s.fb.data()), nullptr))
-        raise(e, "cornelis_cuda_resolve");
-
     onProgress(final, aborted ? RenderStatus::Aborted : RenderStatus::Done);
     if (o.saveImage)
         saveImage(s.fb, o.outputPath);

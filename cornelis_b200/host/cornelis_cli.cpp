@@ -123,6 +123,7 @@ static void usage() {
     std::puts("usage: cornelis [--width W] [--height H] [--spp N] [--aspect A] [--seed S] [--max-depth D]\n"
               "                [--devices G] [--pool P] [--output file.png] [--no-save] [--drop-nonfinite] [--quiet]\n"
               "                [--scene cornell|spheres] [--spheres N] [--accel auto|none|grid]\n"
+              "                [--progressive] [--time-budget SECONDS]   (spp is then the upper limit)\n"
               "defaults reproduce the reference CLI: the Cornell box, 512x512, 4096 spp, cornelisrender2.png");
 }
 
@@ -154,6 +155,8 @@ int main(int argc, char *argv[]) {
         else if (a == "--no-save") options.saveImage = false;
         else if (a == "--drop-nonfinite") options.dropNonFinite = true;
         else if (a == "--quiet") quiet = true;
+        else if (a == "--progressive") options.progressive = true;
+        else if (a == "--time-budget") options.timeBudgetSeconds = std::atof(next());
         else if (a == "--scene") sceneName = next();
         else if (a == "--spheres") sphereCount = static_cast<std::size_t>(std::atoll(next()));
         else if (a == "--accel") {
@@ -191,7 +194,7 @@ int main(int argc, char *argv[]) {
         if (!quiet)
             std::printf("%dx%d, %d spp, %d device(s): %.3f s wall, %.3f s on the GPU, %.1f Msamples/s, %.1f Mrays/s, "
                         "%.3f rays/sample, deepest path %u%s%s\n",
-                        options.width, options.height, options.samplesAA, options.devices, wall, st.gpuSeconds,
+                        options.width, options.height, st.samplesPerPixel, options.devices, wall, st.gpuSeconds,
                         st.pixelSamples / st.gpuSeconds / 1e6, st.rays / st.gpuSeconds / 1e6,
                         static_cast<double>(st.rays) / static_cast<double>(st.pixelSamples), st.maxDepth,
                         options.saveImage ? ", wrote " : "", options.saveImage ? options.outputPath.c_str() : "");

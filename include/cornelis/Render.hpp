@@ -34,7 +34,9 @@ struct RenderStatistics {
     std::uint64_t passes = 0;
     std::uint64_t kernelLaunches = 0;
     std::uint32_t maxDepth = 0;
-    double gpuSeconds = 0.0; // slowest device
+    double gpuSeconds = 0.0; // slowest device (summed over the slices of a progressive render)
+    std::int32_t samplesPerPixel = 0; // samples the frame buffer holds: samplesAA unless aborted or out of time budget
+    std::uint32_t slices = 0;         // sample slices rendered (1 unless progressive)
 };
 
 class RenderError : public std::runtime_error {

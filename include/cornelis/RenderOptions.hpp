@@ -28,6 +28,15 @@ struct RenderOptions {
     std::int32_t devices = 1;        // GPUs of this box to shard the samples over
     std::int32_t poolPaths = 0;      // paths in flight per GPU (0 = library default)
     Acceleration acceleration = Acceleration::Auto;
+    // Progressive rendering (the reference's milestone "progressive/time-budgeted mode", README.md:33, on top of
+    // sample-range rendering): the samples are rendered in growing slices of the global sample index range, the
+    // frame buffer holds the estimate of all samples so far after every slice, and the progress callback runs after
+    // every slice (it may read RenderSession::frameBuffer()).  With a time budget the render stops when the next slice
+    // would overrun it — samplesAA is then the upper limit — and RenderStatistics::samplesPerPixel tells how many
+    // samples the image holds.  Because random numbers are keyed by the global sample index, a progressive render that
+    // runs to samplesAA traces exactly the paths of the one-shot render.
+    bool progressive = false;
+    double timeBudgetSeconds = 0.0;  // > 0 implies progressive
     bool dropNonFinite = false;      // skip NaN/inf path contributions (the reference lets them through)
     bool saveImage = true;           // write the PNG at the end of render(), as the reference does
     std::string outputPath = "cornelisrender2.png";

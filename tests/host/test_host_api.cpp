@@ -3,6 +3,7 @@
 // test_SceneDescription.cpp) with a tiny local CHECK macro.  `cpu` runs what needs no GPU; `gpu` additionally drives
 // RenderSession::render() end to end through the C-ABI.
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -259,6 +260,62 @@ static void testRenderSession(int devices) {
         return RenderCommand::Abort;
     });
     CHECK(aborted == 1);
+
+    // progressive: slices of the global sample range (n, n, 2n, 4n, ...), an image after every slice, and at the end
+    // exactly the paths of the one-shot render (random numbers are keyed by the global sample index)
+    RenderOptions prog = o;
+    prog.progressive = true;
+    prog.saveImage = false;
+    RenderSession progressive(smallScene(), prog);
+    int running = 0, finished = 0;
+    std::uint64_t lastDone = 0;
+    bool monotone = true, imageEachSlice = true;
+    progressive.render([&](RenderProgress const &p, RenderStatus const &st) {
+        monotone = monotone && p.samplesDone > lastDone && p.samplesDone <= p.samplesTotal;
+        lastDone = p.samplesDone;
+        if (st == RenderStatus::Running) {
+            running++;
+            double energy = 0;
+            for (auto const &px : progressive.frameBuffer())
+                energy += px(0) + px(1) + px(2);
+            imageEachSlice = imageEachSlice && std::isfinite(energy) && energy > 0.0;
+        }
+        if (st == RenderStatus::Done)
+            finished++;
+        return RenderCommand::Continue;
+    });
+    CHECK(monotone && imageEachSlice && finished == 1 && running >= 3);
+    CHECK(progressive.statistics().samplesPerPixel == 64 && progressive.statistics().slices == static_cast<unsigned>(running) + 1u);
+    CHECK(progressive.statistics().pixelSamples == 96u * 64u * 64u && progressive.statistics().rays == session.statistics().rays);
+    diff = 0;
+    for (int j = 0; j < 64; j++)
+        for (int i = 0; i < 96; i++)
+            diff = std::max(diff, static_cast<double>(std::fabs(progressive.frameBuffer()(i, j)(0) - fb(i, j)(0))));
+    CHECK(diff < 1e-4);
+
+    // time budget: samplesAA is only the upper limit; the image holds samplesPerPixel samples and is an unbiased
+    // estimate of the same picture
+    RenderOptions timed = o;
+    timed.samplesAA = 1 << 20;
+    timed.timeBudgetSeconds = 0.15;
+    timed.saveImage = false;
+    timed.dropNonFinite = true; // half a million spp meet the reference's NaN (|w.z| > 1 in Oren-Nayar) a few times
+    RenderSession budgeted(smallScene(), timed);
+    auto const t0 = std::chrono::steady_clock::now();
+    budgeted.render();
+    double const took = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    auto const &bs = budgeted.statistics();
+    CHECK(bs.samplesPerPixel >= devices && bs.samplesPerPixel < (1 << 20) && bs.slices >= 2);
+    CHECK(bs.pixelSamples == 96ull * 64ull * static_cast<unsigned long long>(bs.samplesPerPixel));
+    CHECK(took < 1.0);
+    double sumBudgeted = 0;
+    for (auto const &px : budgeted.frameBuffer())
+        sumBudgeted += px(0) + px(1) + px(2);
+    double sumOneShot = 0;
+    for (auto const &px : fb)
+        sumOneShot += px(0) + px(1) + px(2);
+    CHECK(std::fabs(sumBudgeted / sumOneShot - 1.0) < 0.15); // the 64-spp one-shot image is the noisy side
+    std::printf("time budget 0.15 s: %d spp in %u slices, %.3f s\n", bs.samplesPerPixel, bs.slices, took);
 
     // samplesAA <= 0: message and silent return, as the reference (Render.cpp:310-313)
     RenderOptions zero = o;
