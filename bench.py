@@ -59,6 +59,9 @@ def parse_args():
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak")
     ap.add_argument("--pool", type=int, default=0, help="paths in flight per GPU (wavefront pipeline; 0 = default)")
     ap.add_argument("--pipeline", choices=["default", "wavefront", "persistent"], default="default")
+    ap.add_argument("--workload", choices=["cornell", "spheres"], default="cornell",
+                    help="spheres = BASELINE.json configs[3] (10 000 spheres); only the reference arm takes it here — "
+                         "tools/bench_config4.py measures the GPU side and calls this for its CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
@@ -135,12 +138,14 @@ class ClockSampler:
 def time_reference(flat, W, H, seconds_target, threads=0):
     """Times the reference's own CPU loop (oracle/_ref: the unmodified sources compiled by oracle/build_ref.sh; the
     C restatement if that library is absent) on a bounded sample of the workload: the full frame at reduced spp
-    (throughput is spp-independent: SURVEY.md section 6).  40x40 tiles: 32x32 does not divide 1080 and trips the
-    reference's FrameTiling spill bug (Tiles.cpp:21-24)."""
+    (throughput is spp-independent: SURVEY.md section 6).  Tiles that divide the frame (40x40 at 1080p): 32x32 does
+    not divide 1080 and trips the reference's FrameTiling spill bug (Tiles.cpp:21-24)."""
     from oracle import loader
     oracle = loader.best()
     scene = oracle.scene(flat)
-    tile = (40, 40) if (W % 40 == 0 and H % 40 == 0) else (32, 32)
+    def dividing(n):  # a tile edge of 16..64 pixels that divides the frame edge (40 for 1920 and 1080), else the edge
+        return 40 if n % 40 == 0 else min((d for d in range(16, 65) if n % d == 0), default=n)
+    tile = (dividing(W), dividing(H))
     probe = scene.render(W, H, 1, tile=tile, threads=threads, stats=True)["stats"]
     rate = probe["pixel_samples"] / probe["seconds"]
     spp = max(1, min(64, int(round(seconds_target * rate / (W * H)))))
@@ -185,11 +190,13 @@ def reference_arm(args, flat):
 # ------------------------------------------------------------------------------------------------- helpers --
 
 def workload_config(args, note=None):
+    scene = ("cornelis CLI Cornell box (5 planes, 4 spheres, layered Oren-Nayar+GGX material)" if args.workload == "cornell"
+             else "10 000 random spheres over a floor, 64 mixed Oren-Nayar / glossy materials")
     cfg = {
-        "workload": (f"cornelis CLI Cornell box (5 planes, 4 spheres, layered Oren-Nayar+GGX material) "
+        "workload": (f"{scene} "
                      f"{args.width}x{args.height}, camera aspect {args.height / args.width:.4f}, {args.spp} spp"
                      f"{' per GPU' if args.scaling == 'weak' else ' total'}, Russian roulette, no depth cap "
-                     f"(BASELINE.json configs[1])"),
+                     f"(BASELINE.json configs[{1 if args.workload == 'cornell' else 3}])"),
         "width": args.width, "height": args.height, "spp": args.spp,
         "sharding": "sample ranges per GPU + one NCCL sum of the float4 framebuffers",
         "l2": "no L2 flush needed: the persistent pipeline keeps path state in registers (the only global traffic is "
@@ -434,7 +441,12 @@ def ours(args, flat):
 def main():
     args = parse_args()
     from cornelis_b200 import scenes
-    flat = scenes.cornell_box(aspect=args.height / args.width)
+    if args.workload == "spheres":
+        if args.impl != "reference":
+            raise SystemExit("--workload spheres: use tools/bench_config4.py for the GPU side")
+        flat = scenes.many_spheres(10000, aspect=args.height / args.width)
+    else:
+        flat = scenes.cornell_box(aspect=args.height / args.width)
     if args.gpus > 1 and "RANK" not in os.environ:
         # convenience: re-launch under torch.distributed.run, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",

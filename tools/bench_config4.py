@@ -7,9 +7,8 @@ reference's CPU loop (oracle/_ref when present, else the oracle port) on a bound
 """
 import argparse
 import json
-import os
+import subprocess
 import sys
-import time
 from pathlib import Path
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
@@ -44,13 +43,16 @@ if not args.no_exhaustive:
                               "mrays_per_s": st["rays"] / st["gpu_ms"] / 1e3, "sample": f"{spp_small} spp"}
     scene.set_acceleration(binding.ACCEL_AUTO)
 if not args.no_cpu:
-    from oracle import loader
-    ora = loader.best()
+    # the reference's CPU loop on a bounded sample of the same frame: bench.py's reference arm (the one place besides
+    # the tests that may run the oracle), on a tenth of the frame in each dimension
     w, h = W // 10, H // 10
-    t0 = time.time()
-    r = ora.scene(scenes.many_spheres(args.spheres, aspect=h / w)).render(w, h, 8, tile=(w // 4 or 1, h // 4 or 1), stats=True)
-    dt = time.time() - t0
-    out["cpu_baseline"] = {"msamples_per_s": r["stats"]["pixel_samples"] / dt / 1e6, "mrays_per_s": r["stats"]["rays"] / dt / 1e6,
-                           "kind": "reference" if ora.kind == "reference" else "port", "cores": os.cpu_count(),
-                           "sample": f"{w}x{h} at 8 spp, {dt:.1f} s"}
+    r = subprocess.run([sys.executable, str(Path(__file__).resolve().parents[1] / "bench.py"), "--impl", "reference",
+                        "--workload", "spheres", "--width", str(w), "--height", str(h), "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True)
+    try:
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        out["cpu_baseline"] = {"msamples_per_s": line["value"], "mrays_per_s": line["mrays_per_s"],
+                               **{k: line["cpu_baseline"][k] for k in ("kind", "cores", "sample")}}
+    except Exception:
+        out["cpu_baseline"] = {"error": (r.stdout + r.stderr)[-300:]}
 print(json.dumps(out))
