@@ -1,7 +1,7 @@
 """Config 4 (BASELINE.json configs[3]): 10 000 random spheres over a 4000x4000 floor, 64 mixed Oren-Nayar / glossy
 materials, 1920x1080 at 1024 spp, max depth 64 — rendered through the uniform grid.  Prints one JSON line with
 pixel-samples/s and rays/s for both pipelines, the exhaustive-scan kernel on a bounded sample beside it, and the
-reference's CPU loop (oracle/_ref when present, else the oracle port) on a bounded sample of the same frame.
+reference's CPU loop on a bounded sample of the same frame, timed by `bench.py --impl reference --workload spheres`.
 
     python tools/bench_config4.py [--spp 1024] [--width 1920 --height 1080] [--no-cpu]
 """
