@@ -191,22 +191,14 @@ __device__ __forceinline__ void shadeScatter(const DevMaterial &mat, V3 P, V3 N,
     dir = wIn;                                                              // Render.cpp:208
     float const c = fabsf(dot(wIn, N));
     float const denom = pdf * prob;
-    // thr *= f * c / denom, Render.cpp:210-213 with RGB / float as three true divisions (Color.cpp:11-17).  One
-    // reciprocal seed serves the three quotients, and zero numerators (black albedo: the light, gold's diffuse part)
-    // stay on the fast path — same bits as the operator (exact_arith.cuh).
-    float const nr = f.r * c, ng = f.g * c, nb = f.b * c;
-    bool const fast = inFastDivisorRange(denom) && (nr == 0.0f || inFastDivideRange(nr)) &&
-                      (ng == 0.0f || inFastDivideRange(ng)) && (nb == 0.0f || inFastDivideRange(nb));
-    if (fast) {
-        float const rD = rcpSeedRefined(denom);
-        thr.r *= divideExactFast0(nr, denom, rD);
-        thr.g *= divideExactFast0(ng, denom, rD);
-        thr.b *= divideExactFast0(nb, denom, rD);
-    } else {
-        thr.r *= nr / denom;
-        thr.g *= ng / denom;
-        thr.b *= nb / denom;
-    }
+    // thr *= f * c / denom, Render.cpp:210-213 (RGB / float = three divisions, Color.cpp:11-17).  The throughput update
+    // belongs to the tolerant tail: one MUFU reciprocal (<= 1 ulp) serves the three quotients.  denom =
+    // pdf * prob >= 0.5 / (2 Pi) * 0.05 > 0 for finite inputs, zero numerators (black albedo: the light, gold's
+    // diffuse part) give zero, NaN stays NaN.
+    float const scale = c * approxRcp(denom);
+    thr.r *= f.r * scale;
+    thr.g *= f.g * scale;
+    thr.b *= f.b * scale;
 }
 
 // Both halves back to back.  u = (RR draw, x0, x1, x2).

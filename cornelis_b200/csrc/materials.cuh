@@ -11,9 +11,8 @@
 // direction is  float(cos_double(a) * b)  (PRNG.hpp:42-45, Materials.hpp:163-168).  The GGX lobe is so peaked for
 // small roughness that a 1-ulp change of wi moves D(h.N) by ~1e-4 relative, so the 1e-5 material parity budget can
 // only be met if wi itself matches to the bit: the device therefore evaluates sincos in double here too and rounds
-// the double product once, like the reference.  (1 - cos)^5 is formed in double and rounded once, which equals
-// glibc's powf except for its ~7e-4 fraction of not-correctly-rounded results.  The Oren-Nayar sines
-// (Materials.hpp:227) only scale the small b_ term and stay in float.
+// the double product once, like the reference.  The Oren-Nayar sines (Materials.hpp:227) only scale the small b_ term
+// and stay in float.
 #pragma once
 
 #include "device_types.h"
@@ -52,15 +51,35 @@ __device__ __forceinline__ float approxRcp(float x) {
 }
 __device__ __forceinline__ float approxDiv(float a, float b) { return a * approxRcp(b); } // (__fdividef adds range scaling)
 
-// x^5 for Schlick's (1 - cos)^5 (Materials.cpp:41 uses std::pow(x, 5.0f)): exact-ish in double, rounded once.
+// Contractions in the TOLERANT tail are written out as explicit fused multiply-adds: the translation unit is compiled
+// with --fmad=false for the exact chains, and one rounding instead of two is within the tail's budget.
+CB_HD float fma1(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(a, b, c);
+#else
+    return a * b + c;
+#endif
+}
+
+// x^5 for Schlick's (1 - cos)^5 (Materials.cpp:41 uses std::pow(x, 5.0f)): exact-ish in double, rounded once, which
+// equals glibc's powf except for its ~7e-4 fraction of not-correctly-rounded results.
 CB_HD float pow5(float x) {
     double d = static_cast<double>(x);
     double d2 = d * d;
     return static_cast<float>(d2 * d2 * d);
 }
 
-// models::schlick(cos_theta, 1.0f, ior), Materials.cpp:38-42, with R0 precomputed per material.
+// models::schlick(cos_theta, 1.0f, ior), Materials.cpp:38-42, with R0 precomputed per material.  EXACT: the layered
+// BRDF weights the diffuse lobe with 1 - F(N.wi) (Materials.hpp:261), which cancels for grazing wi — one ulp of F is
+// 6e-8 / (1 - F) of the weight.
 CB_HD float schlick(float cosTheta, float r0) { return r0 + (1.0f - r0) * pow5(1.0f - cosTheta); }
+
+// The same for the Fresnel factor of the half vector, which only multiplies the glossy term: tolerant (three float
+// products, one fused multiply-add; within 3 ulp).
+CB_HD float schlickApprox(float cosTheta, float r0) {
+    float const x = 1.0f - cosTheta, x2 = x * x;
+    return fma1(1.0f - r0, x2 * x2 * x, r0);
+}
 
 // models::distributionGTR2, Materials.cpp:16-26 (std::pow(x, 2.0f) is folded to x*x by the reference's compiler).
 // The argument chain up to `base` is exact; the reciprocal is tolerant.
@@ -77,7 +96,7 @@ __device__ __forceinline__ float lambdaTR(float tanTheta, float alpha) {
     if (isinf(tanTheta))
         return 0.0f;
     float k = fabsf(tanTheta) * alpha;
-    return (-1.0f + approxSqrt(1.0f + k * k)) * 0.5f;
+    return fma1(approxSqrt(fma1(k, k, 1.0f)), 0.5f, -0.5f);
 }
 
 // models::shadowMaskingTR, Materials.cpp:34-36.
@@ -103,10 +122,11 @@ __device__ __forceinline__ RGBf orenNayarEval(const DevMaterial &m, V3 wi, V3 wo
     float sO = sqrtf(1.0f - cO * cO);
     float rI = wi.x / sI;
     float rO = wo.x / sO;
-    float cosD = rI * rO + approxSqrt(1.0f - rI * rI) * approxSqrt(1.0f - rO * rO);
+    // (the sign of 1 - r^2, hence the NaN that switches the b-term off, is the same fused or not: r^2 > 1 iff |r| > 1)
+    float cosD = fma1(approxSqrt(fma1(-rI, rI, 1.0f)), approxSqrt(fma1(-rO, rO, 1.0f)), rI * rO);
     bool const thetaONaN = !(fabsf(cO) <= 1.0f);
     float sinProduct = sI * (thetaONaN ? sI : sO);
-    float s = m.on_a + m.on_b * stdMax(0.0f, cosD) * sinProduct;
+    float s = fma1(m.on_b * stdMax(0.0f, cosD), sinProduct, m.on_a);
     return RGBf{m.dr, m.dg, m.db} * s;
 }
 
@@ -132,10 +152,10 @@ __device__ __forceinline__ float glossyEvalPdf(const DevMaterial &m, V3 wi, V3 w
         return 0.0f;
     if (isAlmostZero(cosThetaH))
         D = distributionGTR2(cosThetaH, m);                // eval has no shortcut for a grazing half vector
-    float const sinThetaO = approxSqrt(1.0f - cosThetaO * cosThetaO);
-    float const sinThetaI = approxSqrt(1.0f - cosThetaI * cosThetaI);
+    float const sinThetaO = approxSqrt(fma1(-cosThetaO, cosThetaO, 1.0f));
+    float const sinThetaI = approxSqrt(fma1(-cosThetaI, cosThetaI, 1.0f));
     float const G = shadowMaskingTR(approxDiv(sinThetaI, cosThetaI), approxDiv(sinThetaO, cosThetaO), m.alpha);
-    float const F = schlick(cosThetaH, m.r0);
+    float const F = schlickApprox(cosThetaH, m.r0);
     return approxDiv(F * D * G, 4.0f * cosThetaO * cosThetaI);
 }
 
@@ -144,11 +164,11 @@ __device__ __forceinline__ float glossyEvalPdf(const DevMaterial &m, V3 wi, V3 w
 __device__ __forceinline__ RGBf layeredEvalPdf(const DevMaterial &m, V3 wi, V3 wo, V3 N, float &pdf) {
     float pdfGlossy;
     float const g = glossyEvalPdf(m, wi, wo, N, pdfGlossy);
-    pdf = 0.5f * (kHemispherePdf + pdfGlossy);
+    pdf = fma1(0.5f, pdfGlossy, 0.5f * kHemispherePdf);
     RGBf const Df = orenNayarEval(m, wi, wo);
     RGBf const Gf = RGBf{m.tr, m.tg, m.tb} * g;
     float const k = 1.0f - schlick(stdMax(0.0f, dot(N, wi)), m.r0);
-    return Df * k + Gf;
+    return RGBf{fma1(Df.r, k, Gf.r), fma1(Df.g, k, Gf.g), fma1(Df.b, k, Gf.b)};
 }
 
 // LayeredBRDF::generateDirection, Materials.hpp:279-293: x2 < 0.5 samples the diffuse lobe UNIFORMLY over the

@@ -274,10 +274,13 @@ def test_bsdf_sample_and_eval(binding, oracle, golden):
         # lobe choice / early-outs are decided by identical comparisons on identical inputs
         assert np.array_equal((a["wi"] == 0).all(1), (b["wi"] == 0).all(1))
         err = np.maximum.reduce([rel_err(a["wi"], b["wi"], 1.0), rel_err(a["pdf"], b["pdf"]), rel_err(a["f"], b["f"])])
+        print(f"bsdf_sample max relative error {err.max():.2e}, wi bit-identical: "
+              f"{bool(np.array_equal(a['wi'].view(np.uint32), b['wi'].view(np.uint32)))}")
         assert err.max() <= REL, (err.max(), int(err.argmax()))
         wi = unit(rng, n)
         a, b = sc.bsdf_eval(mat, wi, wo, N), osc.bsdf_eval(mat, wi, wo, N)
         err = np.maximum(rel_err(a["f"], b["f"]), rel_err(a["pdf"], b["pdf"]))
+        print(f"bsdf_eval max relative error {err.max():.2e} (budget {REL:.0e})")
         assert err.max() <= REL, (err.max(), int(err.argmax()))
         assert not np.isnan(a["f"]).any()
 
