@@ -634,6 +634,7 @@ int cornelis_cuda_render_accumulate(cornelis_cuda_scene *s, const cornelis_rende
             uint64_t const limit = std::min(total, done + slice);
             unsigned long long const start = done;
             CB_CUDA(cudaMemcpyAsync(s->claimCursor.ptr, &start, sizeof start, cudaMemcpyHostToDevice, st));
+            cfg.claim = persistentClaim(limit - done, s->gridPersistent);
             launchPersistent(st, s->shape, s->gridPersistent, cfg, s->view, s->claimCursor.ptr, limit, s->accum.ptr,
                              variance ? s->accum2.ptr : nullptr, drop, s->control.ptr);
             launches += 1;

@@ -135,7 +135,7 @@ struct RenderConfig {
     uint32_t maxDepth;  // 0 = unlimited
     uint32_t poolPaths;
     uint32_t variance;  // accumulate second moments
-    uint32_t pad;
+    uint32_t claim;     // persistent pipeline: camera paths a warp claims per atomic (a multiple of 32)
     uint32_t key0, key1; // Philox key = seed
     float dx, dy;       // 1.0f / width, 1.0f / height (Render.cpp:31)
     FastDiv byWidth;    // pixel -> row without a software divide

@@ -23,7 +23,7 @@
 
 namespace cornelis_b200 {
 
-constexpr unsigned long long kClaim = 1024; // camera paths a warp claims per atomic
+constexpr unsigned long long kMaxClaim = 1024; // camera paths a warp claims per atomic (RenderConfig::claim <= this)
 
 // CTA shape of the persistent kernels, measured on B200 with the queued variant (Cornell 1080p, Msamples/s):
 //   256 threads x 4 CTAs/SM (64 registers, 32 warps/SM) 6332     256 x 3 (80 registers, 24 warps) 7103
@@ -70,9 +70,9 @@ __global__ void __launch_bounds__(kPersistentThreads, CORNELIS_PERSISTENT_MIN_BL
             unsigned const avail = static_cast<unsigned>(stashEnd - stashNext);
             unsigned long long fresh = 0;
             uint32_t freshPix = 0, freshSmp = 0;
-            if (count > avail) { // refill: one atomic for the next kClaim paths; one 64-bit division per refill
+            if (count > avail) { // refill: one atomic for the next cfg.claim paths; one 64-bit division per refill
                 if (lane == 0) {
-                    fresh = atomicAdd(cursor, kClaim);
+                    fresh = atomicAdd(cursor, static_cast<unsigned long long>(cfg.claim));
                     unsigned long long const q = fresh / cfg.npixels;
                     freshSmp = static_cast<uint32_t>(q);
                     freshPix = static_cast<uint32_t>(fresh - q * cfg.npixels);
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kPersistentThreads, CORNELIS_PERSISTENT_MIN_BL
             }
             if (count > avail) {
                 stashNext = fresh + (count - avail);
-                stashEnd = fresh + kClaim;
+                stashEnd = fresh + cfg.claim;
                 stashPix = freshPix + (count - avail);
                 stashSmp = freshSmp;
             } else {
@@ -250,17 +250,17 @@ __global__ void __launch_bounds__(kPersistentThreads, CORNELIS_PERSISTENT_MIN_BL
             __syncwarp(); // the slots read here are overwritten by this iteration's pushes
         } else if (camerasLeft) {
             // ---- generateCameraRays (Render.cpp:85-100) for 32 consecutive camera paths ----
-            if (stashNext == stashEnd) { // one atomic per kClaim paths per warp; one 64-bit division per refill
+            if (stashNext == stashEnd) { // one atomic per cfg.claim paths per warp; one 64-bit division per refill
                 unsigned long long fresh = 0;
                 uint32_t freshPix = 0, freshSmp = 0;
                 if (lane == 0) {
-                    fresh = atomicAdd(cursor, kClaim);
+                    fresh = atomicAdd(cursor, static_cast<unsigned long long>(cfg.claim));
                     unsigned long long const q = fresh / cfg.npixels;
                     freshSmp = static_cast<uint32_t>(q);
                     freshPix = static_cast<uint32_t>(fresh - q * cfg.npixels);
                 }
                 stashNext = __shfl_sync(kFull, fresh, 0);
-                stashEnd = stashNext + kClaim;
+                stashEnd = stashNext + cfg.claim;
                 stashPix = __shfl_sync(kFull, freshPix, 0);
                 stashSmp = __shfl_sync(kFull, freshSmp, 0);
             }
@@ -397,6 +397,20 @@ static cudaError_t configureOne(LaunchShape &shape, int &grid) {
             blocks = std::atoi(env);
     grid = shape.numSMs * (blocks > 0 ? blocks : 1);
     return cudaSuccess;
+}
+
+// Camera paths a warp claims per atomic: 1024 for long renders (one 64-bit division per claim), fewer for short ones
+// so that every warp of the grid gets at least ~8 claims and the last claim of the slowest warp is a small part of the
+// launch.  Always a multiple of 32: the queued variant hands out whole batches.
+uint32_t persistentClaim(unsigned long long paths, int grid) {
+    unsigned long long const warps = static_cast<unsigned long long>(grid) * kPersistentWarps;
+    unsigned long long claim = paths / (warps * 8ull);
+    claim = claim / 32ull * 32ull;
+    if (claim < 32ull)
+        claim = 32ull;
+    if (claim > kMaxClaim)
+        claim = kMaxClaim;
+    return static_cast<uint32_t>(claim);
 }
 
 cudaError_t configurePersistent(LaunchShape &shape, bool gridScene, int &grid) {

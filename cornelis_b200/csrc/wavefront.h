@@ -29,6 +29,7 @@ cudaError_t configureKernels(LaunchShape &shape);
 
 // persistent-thread pipeline (persistent.cu)
 cudaError_t configurePersistent(LaunchShape &shape, bool gridScene, int &grid);
+uint32_t persistentClaim(unsigned long long paths, int grid); // RenderConfig::claim for a launch over `paths` camera paths
 void launchPersistent(cudaStream_t s, const LaunchShape &shape, int grid, const RenderConfig &cfg, const SceneView &scene,
                       unsigned long long *cursor, unsigned long long limit, float4 *accum, float4 *accum2,
                       bool dropNonFinite, Control *ctl);
