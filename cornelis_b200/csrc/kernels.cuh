@@ -79,11 +79,24 @@ __device__ __forceinline__ SharedScene stageScene(const SceneView &scene, unsign
 // the instantiation from SceneView::grid.enabled) so the few-primitive kernels keep their register budget.
 template <bool kGrid, int kSphereUnroll = 1>
 __device__ __forceinline__ void closestHitScene(bool live, V3 o, V3 d, const SharedScene &sh, const SceneView &scene,
-                                                float &tBest, int32_t &primBest) {
+                                                float &tBest, int32_t &primBest, const float4 *pairs = nullptr,
+                                                PackedConstants neutral = PackedConstants{1.0f, -0.0f}) {
     if (kGrid)
         closestHitGrid(live, o, d, scene, sh.planes, tBest, primBest);
     else
-        closestHit<kSphereUnroll>(live, o, d, sh, scene, tBest, primBest);
+        closestHit<kSphereUnroll>(live, o, d, sh, scene, tBest, primBest, pairs, neutral);
+}
+
+// The sphere table of a staged scene once more, as pairs for scanSpheresPacked (geometry.cuh):
+//     (cx_2p, cx_2p+1, cy_2p, cy_2p+1), (cz_2p, cz_2p+1, r2_2p, r2_2p+1)      for p < nSpheres / 2
+__device__ __forceinline__ void stageSpherePairs(const SharedScene &sh, uint32_t nSpheres, float4 *pairs) {
+    const float4 *spheres4 = reinterpret_cast<const float4 *>(sh.spheres);
+    for (uint32_t p = threadIdx.x; p < nSpheres / 2u; p += blockDim.x) {
+        float4 const a = spheres4[2u * p], b = spheres4[2u * p + 1u];
+        pairs[2u * p] = make_float4(a.x, b.x, a.y, b.y);
+        pairs[2u * p + 1u] = make_float4(a.z, b.z, a.w, b.w);
+    }
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------ compaction --

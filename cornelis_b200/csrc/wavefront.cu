@@ -405,15 +405,20 @@ __global__ void __launch_bounds__(kBlockThreads) k_pixel_rays(DevCamera cam, uin
 // The intersect stage on a plain float4 ray batch — the same closestHit as k_intersect without the queues.
 // Used by cornelis_cuda_intersect(_device): parity tests and the intersection microbench (config 3).
 #ifndef CORNELIS_BATCH_SPHERE_GROUP
-#define CORNELIS_BATCH_SPHERE_GROUP 8 // spheres per discriminant vote (geometry.cuh scanSpheres)
+#define CORNELIS_BATCH_SPHERE_GROUP 16 // spheres per discriminant vote (geometry.cuh scanSpheres)
 #endif
 template <bool kGrid>
 __global__ void __launch_bounds__(kBlockThreads) k_intersect_batch(SceneView scene, size_t n,
                                                                    const float4 *__restrict__ org,
                                                                    const float4 *__restrict__ dir,
-                                                                   HitRecord *__restrict__ hits) {
+                                                                   HitRecord *__restrict__ hits, uint32_t pairOffset,
+                                                                   PackedConstants neutral) {
     extern __shared__ __align__(16) unsigned char smem[];
     SharedScene const sh = stageScene<kGrid>(scene, smem, false);
+    // pairOffset != 0: room for the paired sphere table behind the staged scene (packed FP32 scan)
+    float4 *pairs = (!kGrid && pairOffset) ? reinterpret_cast<float4 *>(smem + pairOffset) : nullptr;
+    if (pairs)
+        stageSpherePairs(sh, scene.nSpheres, pairs);
     for (size_t base = static_cast<size_t>(blockIdx.x) * blockDim.x; base < n;
          base += static_cast<size_t>(gridDim.x) * blockDim.x) {
         size_t const i = base + threadIdx.x;
@@ -425,7 +430,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_intersect_batch(SceneView sce
         }
         float t = INFINITY;
         int32_t prim = -1;
-        closestHitScene<kGrid, CORNELIS_BATCH_SPHERE_GROUP>(valid, V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, sh, scene, t, prim);
+        closestHitScene<kGrid, CORNELIS_BATCH_SPHERE_GROUP>(valid, V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, sh, scene, t,
+                                                            prim, pairs, neutral);
         if (valid)
             hits[i] = HitRecord{t, prim};
     }
@@ -663,12 +669,18 @@ void launchPixelRays(cudaStream_t s, const LaunchShape &shape, const DevCamera &
 
 void launchIntersectBatch(cudaStream_t s, const LaunchShape &shape, const SceneView &scene, size_t n,
                           const float4 *org, const float4 *dir, HitRecord *hits) {
-    if (scene.grid.enabled)
+    if (scene.grid.enabled) {
         k_intersect_batch<true><<<gridFor(n, shape.numSMs, shape.blocksPerSM), kBlockThreads, shape.sceneSmemBytes, s>>>(
-            scene, n, org, dir, hits);
-    else
-        k_intersect_batch<false><<<gridFor(n, shape.numSMs, shape.blocksPerSM), kBlockThreads, shape.sceneSmemBytes, s>>>(
-            scene, n, org, dir, hits);
+            scene, n, org, dir, hits, 0u, hostPackedConstants());
+        return;
+    }
+    // the exhaustive scan runs on packed FP32 when the paired copy of the sphere table fits behind the staged scene
+    size_t const pairOffset = (shape.sceneSmemBytes + 15u) & ~static_cast<size_t>(15u);
+    size_t const withPairs = pairOffset + sizeof(float4) * (scene.nSpheres & ~1u);
+    bool const packed = shape.batchPacked && scene.nSpheres >= 2u && withPairs <= shape.smemOptin;
+    k_intersect_batch<false><<<gridFor(n, shape.numSMs, shape.blocksPerSM), kBlockThreads,
+                               packed ? withPairs : shape.sceneSmemBytes, s>>>(
+        scene, n, org, dir, hits, packed ? static_cast<uint32_t>(pairOffset) : 0u, hostPackedConstants());
 }
 
 void launchHitSurface(cudaStream_t s, const LaunchShape &shape, const SceneView &scene, size_t n, const float4 *org,
@@ -741,6 +753,15 @@ cudaError_t configureKernels(LaunchShape &shape) {
             return e;
         if ((e = cudaFuncSetAttribute(k_hit_surface<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
             return e;
+    }
+    {   // the batch kernel may add a paired copy of the sphere table (launchIntersectBatch)
+        size_t const most = shape.smemOptin;
+        if (most > 48 * 1024)
+            if ((e = cudaFuncSetAttribute(k_intersect_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(most))) != cudaSuccess)
+                return e;
+        if (const char *env = std::getenv("CORNELIS_BATCH_PACKED"))
+            shape.batchPacked = std::atoi(env) != 0;
     }
     auto resident = [&](auto kernel, size_t smem, int &grid) -> cudaError_t {
         int blocks = 0;

@@ -194,6 +194,31 @@ def test_rays_starting_on_planes_keep_the_sign_of_zero(binding, oracle):
     assert zero.sum() > n // 4 and np.signbit(b["t"][zero]).any() and (~np.signbit(b["t"][zero])).any()
 
 
+def test_packed_fp32_scan_is_bit_identical(binding, oracle, monkeypatch):
+    """cornelis_cuda_intersect scans the spheres two at a time on packed FP32 (FFMA2, csrc/packed_f32.cuh): every packed
+    operation must be the scalar IEEE operation on the same operands.  Checked against the scalar scan of the same
+    library (CORNELIS_BATCH_PACKED=0 at scene creation) on the microbench scene and against the oracle for odd and
+    tiny sphere counts (the last sphere of an odd table has no partner; groups of 16 leave a remainder)."""
+    org, dirs = scenes.microbench_rays(1 << 19)
+    flat = scenes.microbench_scene(1024)
+    packed = binding.Scene(flat)
+    packed.set_acceleration(binding.ACCEL_NONE)
+    a = packed.intersect(org, dirs, surface=False)
+    monkeypatch.setenv("CORNELIS_BATCH_PACKED", "0")
+    scalar = binding.Scene(flat)
+    scalar.set_acceleration(binding.ACCEL_NONE)
+    b = scalar.intersect(org, dirs, surface=False)
+    monkeypatch.delenv("CORNELIS_BATCH_PACKED")
+    assert np.array_equal(a["prim"], b["prim"]) and bit_equal(a["t"], b["t"])
+    assert (a["prim"] >= 0).all() and (a["prim"] < 1024).mean() > 0.2
+    for count in (1, 2, 3, 17, 33, 1023):
+        flat = scenes.microbench_scene(count)
+        sc = binding.Scene(flat)
+        sc.set_acceleration(binding.ACCEL_NONE)
+        got, ref = sc.intersect(org[:20000], dirs[:20000], surface=False), oracle.scene(flat).intersect(org[:20000], dirs[:20000])
+        assert np.array_equal(got["prim"], ref["prim"]) and bit_equal(got["t"], ref["t"]), count
+
+
 def test_rays_on_and_tangent_to_spheres(binding, oracle):
     """Zero numerators of the sphere test (Geometry.cpp:77-84): an origin exactly on a sphere (C == r^2), a direction
     perpendicular to the centre offset (B == 0), both at once (t = 0 from a zero discriminant) and exact tangents.
