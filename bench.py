@@ -38,13 +38,13 @@ FLOP_PER_SURVIVING_BOUNCE = 250
 FLOP_PER_KILLED_HIT = 12
 # bytes per item of the wavefront layout (DESIGN.md "Data layout"): see roofline() below
 # DRAM traffic of the persistent kernel from the committed ncu capture (profiles/r1_queue/
-# ncu_full_summary_k_persistent_queued_cornell_512spp.txt): dram__bytes_read.sum + dram__bytes_write.sum = 32.90 MB +
-# 0.12 MB for one launch of 1920x1080 x 512 spp.  The only global traffic is framebuffer atomics over a 33 MB image
+# ncu_full_summary_k_persistent_queued_cornell_512spp.txt): dram__bytes_read.sum + dram__bytes_write.sum = 32.49 MB +
+# 0.09 MB for one launch of 1920x1080 x 512 spp.  The only global traffic is framebuffer atomics over a 33 MB image
 # that lives in the 126 MB L2, so DRAM sees one read of the image per launch whatever the sample count (a 64-spp
 # launch: 31.65 MB + 0.02 MB): the figure is reported as captured, not scaled.
-NCU_PERSISTENT_DRAM_BYTES = 32.897280e6 + 0.121856e6
-NCU_PERSISTENT_ISSUE = {"busy_pct": 84.6, "warp_instructions_per_ray": 38.0, "lanes_per_instruction": 29.0,
-                        "no_instruction_stall_per_issue": 0.69, "registers": 72, "ctas_per_sm": "7 x 128 threads"}
+NCU_PERSISTENT_DRAM_BYTES = 32.489472e6 + 0.090624e6
+NCU_PERSISTENT_ISSUE = {"busy_pct": 84.8, "warp_instructions_per_ray": 37.1, "lanes_per_instruction": 28.95,
+                        "no_instruction_stall_per_issue": 0.64, "registers": 72, "ctas_per_sm": "7 x 128 threads"}
 
 
 def parse_args():
