@@ -83,8 +83,9 @@ enum {
     CORNELIS_PIPELINE_WAVEFRONT = 1, /* raygen -> intersect(+compact) -> shade(+compact) -> accumulate kernels over
                                         a path pool in HBM; with the grid the intersect stage is a kernel of warps
                                         that pull rays from the pool plus a streaming compaction pass */
-    CORNELIS_PIPELINE_PERSISTENT = 2 /* the same stage functions with each path held in its thread's registers and
-                                        finished lanes refilled by a warp-level claim */
+    CORNELIS_PIPELINE_PERSISTENT = 2 /* the same stage functions in ONE persistent kernel: a path lives in registers,
+                                        Russian-roulette survivors wait in a warp-private shared-memory queue and are
+                                        scattered 32 at a time, free warps start 32 camera paths (no pool in HBM) */
 };
 
 typedef struct cornelis_render_params {
