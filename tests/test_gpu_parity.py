@@ -519,6 +519,22 @@ def test_handle_churn_reuses_device_memory(binding):
         assert np.allclose(images[0], img, rtol=1e-5, atol=1e-6)  # same paths; atomics reorder the fp32 sums
 
 
+def test_lane_refill_variant_traces_the_same_paths(binding, monkeypatch):
+    """The persistent kernel without the queues (kept for scenes whose tables leave no shared memory for them;
+    CORNELIS_PERSISTENT_QUEUE=0 selects it at scene creation) accounts for the same paths as the queued one."""
+    queued = binding.Scene(scenes.cornell_box())
+    monkeypatch.setenv("CORNELIS_PERSISTENT_QUEUE", "0")
+    refill = binding.Scene(scenes.cornell_box())
+    monkeypatch.delenv("CORNELIS_PERSISTENT_QUEUE")
+    for (w, h, spp, depth) in [(96, 64, 32, 0), (7, 5, 9, 0), (64, 64, 16, 3)]:
+        a = queued.render_accumulate(w, h, spp, pipeline=2, max_depth=depth)
+        img_a = queued.resolve(spp).copy()
+        b = refill.render_accumulate(w, h, spp, pipeline=2, max_depth=depth)
+        for key in ("pixel_samples", "rays", "shaded_hits", "max_depth", "contributions"):
+            assert a[key] == b[key], (w, h, spp, key)
+        assert np.allclose(img_a, refill.resolve(spp), rtol=1e-5, atol=1e-6)
+
+
 def test_persistent_batches_of_any_size(binding):
     """The persistent kernel parks Russian-roulette survivors per warp and scatters them 32 at a time; frames with
     fewer pixels than a warp, sample ranges that end inside a warp's claim, and the final partial batches must
