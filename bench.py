@@ -200,7 +200,7 @@ def workload_config(args, note=None):
         "width": args.width, "height": args.height, "spp": args.spp,
         "sharding": "sample ranges per GPU + one NCCL sum of the float4 framebuffers",
         "l2": "no L2 flush needed: the persistent pipeline keeps path state in registers (the only global traffic is "
-              "scattered framebuffer atomics over a 33 MB image); the wavefront pipeline's pool + queues (>= 600 MB) "
+              "scattered framebuffer atomics over a 33 MB image); the wavefront pipeline's pool + queues (2.9 GB) "
               "exceed the 126 MB L2",
         "seed": 19791102,
     }

@@ -563,10 +563,11 @@ int cornelis_cuda_render_accumulate(cornelis_cuda_scene *s, const cornelis_rende
         return fail(CORNELIS_ERR_INVALID_ARGUMENT, "unknown pipeline");
     bool const persistent = pipeline == CORNELIS_PIPELINE_PERSISTENT;
 
-    // Paths in flight.  2^22 keeps every stage launch above 100 k threads.  Grid scenes take
-    // 2^24 (2.9 GB of pool and queues): a pass of k_walk ends with a few warps still on their longest walks, and
-    // that tail is a fifth of a 2^22-ray pass (config 4: 1262 -> 1472 Msamples/s; 2^26 would give 1535).
-    uint32_t pool = p->pool_paths > 0 ? static_cast<uint32_t>(p->pool_paths) : s->view.grid.enabled ? (1u << 24) : (1u << 22);
+    // Paths in flight: 2^24 (2.9 GB of pool and queues out of 180 GB).  A pass is five or six dependent launches, each
+    // of which has to drain before the next starts, and a pass of k_walk ends with a few warps still on their longest
+    // walks; with 2^22 paths those per-pass costs were 8 % of the Cornell wavefront render (4867 -> 5251 Msamples/s) and
+    // 17 % of config 4 (1262 -> 1473); 2^26 would add another 2-4 %.
+    uint32_t pool = p->pool_paths > 0 ? static_cast<uint32_t>(p->pool_paths) : (1u << 24);
     if (const char *env = std::getenv("CORNELIS_POOL_PATHS"))
         if (p->pool_paths <= 0 && std::atoll(env) > 0)
             pool = static_cast<uint32_t>(std::atoll(env));
