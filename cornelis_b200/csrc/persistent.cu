@@ -1,21 +1,25 @@
-// Persistent-thread variant of the render loop: the same stage functions as the wavefront kernels (raygen,
-// closestHit, shadeBounce, per-pixel accumulation), but a path lives in its thread's registers from its camera ray
-// to its end and the lane that held it is refilled at once.
+// Persistent-thread pipeline of the render loop: the same stage functions as the wavefront kernels (camera rays,
+// closestHit, the two halves of accumulateAndBounce, per-pixel accumulation) in ONE kernel whose paths never leave the
+// SM.  Two variants:
+//   k_persistent_queued (default)  Russian-roulette survivors wait in a warp-private shared-memory queue; the BSDF half
+//                                  runs on full batches of 32, free warps start 32 camera paths (see below)
+//   k_persistent                   a path stays in its lane from camera ray to its end and the lane is refilled at once;
+//                                  kept for scenes whose tables leave no shared memory for the queues
 //
 // Why: ncu on the wavefront kernels (profiles/) shows both compute stages bound by instruction latency at ~0.65 issued
 // instructions per cycle per scheduler — a third of every warp's stall time is waiting for the pool's global loads
 // and for the block barriers of the compaction, and ~20 % of the issued instructions move path state and queue
 // entries.  For scenes whose primitives fit in shared memory none of that traffic is needed.
 //
-// What replaces the wavefront's machinery:
+// What replaces the wavefront's machinery in k_persistent:
 //   * pool + compaction (reference Render.cpp:142-149, :215-217): a lane whose path ended (miss, Russian roulette,
 //     depth cap) claims the next camera path.  The claim is a warp operation: ballot of the lanes that need a path,
-//     popc prefix for each lane's offset, ONE atomicAdd on the global cursor per 1024 camera paths per warp (a
-//     warp-private stash of indices), so the lanes of a warp stay full without any queue.
+//     popc prefix for each lane's offset, ONE atomicAdd on the global cursor per claim of up to 1024 camera paths per
+//     warp (a warp-private stash of indices), so the lanes of a warp stay full without any queue.
 //   * accumulate kernel (Render.cpp:245-248): the path's radiance is added to its pixel when the path ends, with
 //     the same 128-bit vector reduction, skipped when it is exactly zero.
 // Path identity, random numbers (Philox keyed by pixel, sample, depth) and all arithmetic are shared with the
-// wavefront pipeline, so both produce the same per-path results; only fp32 summation order in the pixel differs.
+// wavefront pipeline, so all of them produce the same per-path results; only fp32 summation order in the pixel differs.
 #include <cstdlib>
 
 #include "kernels.cuh"
