@@ -82,7 +82,7 @@ def build_host(force: bool = False):
     core = LIB / "libcorneliscore.so"
     if force or _stale(core, [*core_srcs, *headers, Path(__file__)]):
         _run([cxx, "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-Wall", "-Wextra", "-shared", *inc, "-o", core,
-              *core_srcs, f"-L{LIB}", "-lcornelis_cuda", "-Wl,-rpath,$ORIGIN", "-pthread"])
+              *core_srcs, f"-L{LIB}", "-lcornelis_cuda", "-lz", "-Wl,-rpath,$ORIGIN", "-pthread"])
     cli_src = HOST / "cornelis_cli.cpp"
     cli = LIB / "cornelis"
     if cli_src.exists() and (force or _stale(cli, [cli_src, core, *headers])):

@@ -325,8 +325,22 @@ static void testRenderSession(int devices) {
     noop.render();
 }
 
+// `png <path> <width> <height>`: saveImage (display transform, quantisation, PNG encoding — no GPU involved) on a
+// deterministic image; tests/test_host_api.py decodes the file and checks every pixel.
+static int writeTestPng(char const *path, int width, int height) {
+    RGBFrameBuffer fb(PixelRect(width, height));
+    for (int j = 0; j < height; j++)
+        for (int i = 0; i < width; i++)
+            fb(i, j) = RGB(static_cast<float>(i) / static_cast<float>(width), static_cast<float>(j) / static_cast<float>(height),
+                           static_cast<float>((i * 7 + j * 13) % 32) / 16.0f); // the third channel exceeds 1 and is noisy
+    saveImage(fb, path);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     std::string const mode = argc > 1 ? argv[1] : "cpu";
+    if (mode == "png" && argc > 4)
+        return writeTestPng(argv[2], std::atoi(argv[3]), std::atoi(argv[4]));
     testCamera();
     testMath();
     testTiles();

@@ -27,6 +27,57 @@ def test_host_api_cpu(host_test_binary):
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+def _decode_png_rgb8(path):
+    """A PNG decoder for 8-bit RGB, non-interlaced files: chunks, zlib, the five row filters."""
+    import struct
+    import zlib
+
+    import numpy as np
+    data = Path(path).read_bytes()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, width, height = 8, b"", 0, 0
+    while pos < len(data):
+        (n,), tag = struct.unpack(">I", data[pos:pos + 4]), data[pos + 4:pos + 8]
+        body = data[pos + 8:pos + 8 + n]
+        assert zlib.crc32(tag + body) == struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])[0], tag
+        if tag == b"IHDR":
+            width, height, depth, colour, _, _, interlace = struct.unpack(">IIBBBBB", body)
+            assert (depth, colour, interlace) == (8, 2, 0)
+        elif tag == b"IDAT":
+            idat += body
+        pos += 12 + n
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(height, 1 + 3 * width)
+    out = np.zeros((height, 3 * width), np.int32)
+    for j in range(height):
+        kind, row = int(raw[j, 0]), raw[j, 1:].astype(np.int32)
+        up = out[j - 1] if j else np.zeros(3 * width, np.int32)
+        for i in range(3 * width):
+            a = out[j, i - 3] if i >= 3 else 0
+            b, c = up[i], (up[i - 3] if i >= 3 else 0)
+            p = a + b - c
+            pa, pb, pc = abs(p - a), abs(p - b), abs(p - c)
+            pred = [0, a, b, (a + b) // 2, a if (pa <= pb and pa <= pc) else b if pb <= pc else c][kind]
+            out[j, i] = (row[i] + pred) & 255
+    return out.reshape(height, width, 3).astype(np.uint8), len(data)
+
+
+def test_save_image_writes_a_real_png(host_test_binary, tmp_path):
+    """saveImage (Render.cpp:257-265): toSRGB, quantizeTo8bit, PNG.  The file must decode to exactly the quantised
+    display values (oracle's toSRGB restatement) and be compressed (the rows are filtered and deflated)."""
+    import numpy as np
+    from oracle import loader
+    W, H = 97, 41
+    out = tmp_path / "gradient.png"
+    r = subprocess.run([str(host_test_binary), "png", str(out), str(W), str(H)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    image, size = _decode_png_rgb8(out)
+    i, j = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32))
+    linear = np.stack([i / np.float32(W), j / np.float32(H), ((i * 7 + j * 13) % 32) / np.float32(16)], axis=2)
+    expect = loader.best().to_srgb8(linear.reshape(-1, 3).astype(np.float32)).reshape(H, W, 3)
+    assert np.array_equal(image, expect)
+    assert size < W * H * 3  # smaller than the raw pixels: the two smooth channels compress
+
+
 def test_cli_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
@@ -48,7 +99,9 @@ def test_cli_renders_reference_default_scene(tmp_path):
     out = tmp_path / "cornell.png"
     r = subprocess.run([str(LIB / "cornelis"), "--spp", "16", "--output", str(out)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "512x512, 16 spp" in r.stdout and out.exists() and out.stat().st_size > 512 * 512 * 3
+    assert "512x512, 16 spp" in r.stdout and out.exists()
+    image, _ = _decode_png_rgb8(out)
+    assert image.shape == (512, 512, 3) and image[:256].mean() > image[256:].mean() * 0.5 and image.max() == 255
 
 
 @pytest.mark.gpu
