@@ -16,7 +16,7 @@ def _run(*args):
 
 
 @pytest.mark.parametrize("workload", ["cornell", "spheres"])
-def test_reference_arm_json_line(workload):
+def test_reference_arm_json_line(workload, port_oracle, ref_oracle):  # the fixtures build the oracle libraries
     r = _run("--impl", "reference", "--workload", workload, "--width", "80", "--height", "40", "--steps", "1",
              "--warmup", "0")
     assert r.returncode == 0, r.stderr

@@ -61,11 +61,10 @@ def _decode_png_rgb8(path):
     return out.reshape(height, width, 3).astype(np.uint8), len(data)
 
 
-def test_save_image_writes_a_real_png(host_test_binary, tmp_path):
+def test_save_image_writes_a_real_png(host_test_binary, tmp_path, port_oracle):
     """saveImage (Render.cpp:257-265): toSRGB, quantizeTo8bit, PNG.  The file must decode to exactly the quantised
     display values (oracle's toSRGB restatement) and be compressed (the rows are filtered and deflated)."""
     import numpy as np
-    from oracle import loader
     W, H = 97, 41
     out = tmp_path / "gradient.png"
     r = subprocess.run([str(host_test_binary), "png", str(out), str(W), str(H)], capture_output=True, text=True)
@@ -73,7 +72,7 @@ def test_save_image_writes_a_real_png(host_test_binary, tmp_path):
     image, size = _decode_png_rgb8(out)
     i, j = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32))
     linear = np.stack([i / np.float32(W), j / np.float32(H), ((i * 7 + j * 13) % 32) / np.float32(16)], axis=2)
-    expect = loader.best().to_srgb8(linear.reshape(-1, 3).astype(np.float32)).reshape(H, W, 3)
+    expect = port_oracle.to_srgb8(linear.reshape(-1, 3).astype(np.float32)).reshape(H, W, 3)
     assert np.array_equal(image, expect)
     assert size < W * H * 3  # smaller than the raw pixels: the two smooth channels compress
 
