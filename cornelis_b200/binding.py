@@ -21,13 +21,17 @@ EXPORTS = [
     "cornelis_cuda_scene_create", "cornelis_cuda_scene_destroy", "cornelis_cuda_scene_set_stream",
     "cornelis_cuda_scene_set_acceleration", "cornelis_cuda_scene_acceleration", "cornelis_cuda_render_accumulate",
     "cornelis_cuda_framebuffer_device", "cornelis_cuda_reduce_framebuffers", "cornelis_cuda_resolve", "cornelis_cuda_resolve_device",
+    "cornelis_cuda_comm_unique_id", "cornelis_cuda_comm_init_rank", "cornelis_cuda_comm_init_all",
+    "cornelis_cuda_comm_destroy", "cornelis_cuda_comm_info", "cornelis_cuda_allreduce_framebuffers",
     "cornelis_cuda_resolve_srgb8",
     "cornelis_cuda_render", "cornelis_cuda_pixel_rays", "cornelis_cuda_intersect",
     "cornelis_cuda_intersect_device", "cornelis_cuda_bsdf_sample", "cornelis_cuda_bsdf_eval",
     "cornelis_cuda_shade", "cornelis_cuda_rng_uniforms", "cornelis_cuda_selftest_arith",
+    "cornelis_cuda_intersect_compact", "cornelis_cuda_selftest_srgb8",
 ]
 
-OK, ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_ABORTED = range(6)
+OK, ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_ABORTED, ERR_NCCL = range(7)
+COMM_ID_BYTES = 128
 RENDER_VARIANCE, RENDER_KEEP, RENDER_STAGE_TIMING, RENDER_DROP_NONFINITE = 1, 2, 4, 8
 PIPELINE_DEFAULT, PIPELINE_WAVEFRONT, PIPELINE_PERSISTENT = 0, 1, 2
 DEFAULT_SEED = 19791102
@@ -102,6 +106,12 @@ def lib():
         L.cornelis_cuda_framebuffer_device.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
         L.cornelis_cuda_resolve.argtypes = [vp, i32, vp, vp]
         L.cornelis_cuda_reduce_framebuffers.argtypes = [C.POINTER(vp), C.c_int]
+        L.cornelis_cuda_comm_unique_id.argtypes = [vp]
+        L.cornelis_cuda_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.cornelis_cuda_comm_init_all.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+        L.cornelis_cuda_comm_destroy.argtypes = [vp]
+        L.cornelis_cuda_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.cornelis_cuda_allreduce_framebuffers.argtypes = [vp, C.POINTER(vp), C.c_int]
         L.cornelis_cuda_resolve_srgb8.argtypes = [vp, i32, vp]
         L.cornelis_cuda_resolve_device.argtypes = [vp, i32, C.POINTER(vp)]
         L.cornelis_cuda_render.argtypes = [vp, C.POINTER(RenderParams), vp, C.POINTER(RenderStats)]
@@ -113,6 +123,8 @@ def lib():
         L.cornelis_cuda_shade.argtypes = [vp, sz, i32, f, f, f, f, f, f, f, f, f]
         L.cornelis_cuda_rng_uniforms.argtypes = [vp, C.c_uint64, sz, f, f, f, f]
         L.cornelis_cuda_selftest_arith.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]
+        L.cornelis_cuda_intersect_compact.argtypes = [vp, sz, f, f, f, C.POINTER(C.c_uint32), f, C.POINTER(C.c_uint32)]
+        L.cornelis_cuda_selftest_srgb8.argtypes = [vp, C.c_uint32, sz, vp]
         _lib = L
     return _lib
 
@@ -134,9 +146,63 @@ def device_count() -> int:
 
 
 def reduce_framebuffers(scene_list):
-    """Sum the accumulators of several scenes (one per GPU, single process) into the first."""
+    """Sum the accumulators of several scenes (single process) into the first: one grouped ncclReduce over the
+    scenes' GPUs (scenes sharing a GPU are added locally first)."""
     arr = (C.c_void_p * len(scene_list))(*[s.handle for s in scene_list])
     _check(lib().cornelis_cuda_reduce_framebuffers(arr, len(scene_list)))
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId: 128 bytes rank 0 hands to the other ranks of a one-process-per-GPU job."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    _check(lib().cornelis_cuda_comm_unique_id(buf))
+    return bytes(buf)
+
+
+class Comm:
+    """An NCCL communicator owned by the library: the framebuffer sum is the render path's only exchange step."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    @classmethod
+    def init_rank(cls, unique_id: bytes, rank: int, n_ranks: int, device: int):
+        """One rank of a one-process-per-GPU job (ncclCommInitRank)."""
+        if len(unique_id) != COMM_ID_BYTES:
+            raise ValueError("unique id must be 128 bytes")
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        h = C.c_void_p()
+        _check(lib().cornelis_cuda_comm_init_rank(buf, rank, n_ranks, device, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def init_all(cls, devices):
+        """All the given GPUs from this one process (ncclCommInitAll)."""
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        _check(lib().cornelis_cuda_comm_init_all(arr, len(devices), C.byref(h)))
+        return cls(h)
+
+    def info(self):
+        n, local, version = C.c_int(0), C.c_int(0), C.c_int(0)
+        _check(lib().cornelis_cuda_comm_info(self.handle, C.byref(n), C.byref(local), C.byref(version)))
+        return dict(n_ranks=n.value, n_local=local.value, nccl_version=version.value)
+
+    def allreduce_framebuffers(self, scene_list):
+        """In-place sum over all ranks of the accumulation images of this process's scenes (enqueued on their streams)."""
+        arr = (C.c_void_p * len(scene_list))(*[s.handle for s in scene_list])
+        _check(lib().cornelis_cuda_allreduce_framebuffers(self.handle, arr, len(scene_list)))
+
+    def close(self):
+        if self.handle:
+            lib().cornelis_cuda_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _ptr(a):
@@ -302,6 +368,23 @@ class Scene:
         _check(lib().cornelis_cuda_intersect(self.handle, n, _ptr(org), _ptr(dirs), _ptr(t), _ptr(prim), _ptr(P), _ptr(N),
                                              _ptr(mat)))
         return dict(t=t, prim=prim, P=P, N=N, mat=mat)
+
+    def intersect_compact(self, org, dirs):
+        """Intersect stage of one wavefront pass incl. compaction: (indices of the rays that hit, of those that missed),
+        each in the order the device queues hold them."""
+        org, dirs = _f32(org, (-1, 3)), _f32(dirs, (-1, 3))
+        n = len(org)
+        hits, misses = np.empty(n, np.uint32), np.empty(n, np.uint32)
+        nh, nm = C.c_uint32(0), C.c_uint32(0)
+        _check(lib().cornelis_cuda_intersect_compact(self.handle, n, _ptr(org), _ptr(dirs), _ptr(hits), C.byref(nh),
+                                                     _ptr(misses), C.byref(nm)))
+        return hits[:nh.value], misses[:nm.value]
+
+    def selftest_srgb8(self, first_bits, n):
+        """Device display transform + quantisation of the floats with bit patterns first_bits .. first_bits + n - 1."""
+        out = np.empty(n, np.uint8)
+        _check(lib().cornelis_cuda_selftest_srgb8(self.handle, first_bits, n, _ptr(out)))
+        return out
 
     def intersect_device(self, n, d_org4, d_dir4, d_hit2, repeats=1):
         ms = C.c_float(0)

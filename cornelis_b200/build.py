@@ -29,6 +29,19 @@ NVCC_FLAGS = [*ARCH, "-lineinfo", "-O3", "--fmad=false", "-std=c++17", "-Xcompil
               "-Xptxas", "-v", *os.environ.get("CORNELIS_NVCC_EXTRA", "").split()]
 
 
+def csrc_hash() -> str:
+    """SHA-256 over the device sources (cornelis_b200/csrc, sorted by name) and the nvcc flags: what a committed ncu
+    capture or ptxas log has to match to describe the kernels that are running."""
+    import hashlib
+    h = hashlib.sha256()
+    for path in sorted(CSRC.iterdir()):
+        if path.suffix in {".cu", ".cuh", ".h"}:
+            h.update(path.name.encode())
+            h.update(path.read_bytes())
+    h.update(" ".join(str(f) for f in NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def _stale(target: Path, sources) -> bool:
     if not target.exists():
         return True
@@ -66,7 +79,7 @@ def build_cuda(force: bool = False) -> Path:
             raise RuntimeError(f"nvcc failed on {src}")
     so = LIB / "libcornelis_cuda.so"
     if force or _stale(so, objs):
-        _run([NVCC, *ARCH, "-shared", "-o", so, *objs, "-Xcompiler", "-fPIC"])
+        _run([NVCC, *ARCH, "-shared", "-o", so, *objs, "-Xcompiler", "-fPIC", "-ldl"])  # NCCL is dlopen'ed (comm.cu)
     return so
 
 

@@ -16,6 +16,7 @@
 #include "device_types.h"
 #include "materials.cuh"
 #include "math.cuh"
+#include "scene_access.h"
 #include "scene_tables.h"
 #include "wavefront.h"
 
@@ -40,7 +41,7 @@ int fail(cornelis_status code, const std::string &message) {
 
 // Device-memory cache.  A render service creates and destroys scene handles all the time (bench.py's end-to-end leg
 // does so every step), and cudaFree / cudaMalloc of the framebuffer-sized blocks cost up to 400 ms per call on the
-// B200 boxes (measured: profiles/r2_queue/e2e_breakdown.txt) — a third of a 1080p, 4096-spp render.  Blocks released
+// B200 boxes (measured: profiles/r1_queue/e2e_breakdown.txt) — a third of a 1080p, 4096-spp render.  Blocks released
 // by a handle are therefore kept per device, keyed by size, and handed to the next request of a similar size;
 // cornelis_cuda_trim_memory() returns them to the driver.  At most kCacheLimitBytes stay cached per process.
 class DeviceCache {
@@ -219,7 +220,8 @@ struct cornelis_cuda_scene {
     Control hostControlStorage{};
     Control *hostControl = &hostControlStorage; // 104 bytes: pageable is fine
     DeviceBuffer<float4> accum, accum2;
-    bool haveVariance = false;
+    bool haveImage = false;    // accum holds the sum of a render of this frame size (what CORNELIS_RENDER_KEEP adds to)
+    bool haveVariance = false; // ... and accum2 the second moments of the same samples
     DeviceBuffer<float> outRgb, outVar;
     DeviceBuffer<uint8_t> outRgb8;
     // staging for the stage entry points
@@ -282,11 +284,21 @@ int ensureFrame(cornelis_cuda_scene *s, uint32_t width, uint32_t height, uint32_
     if (resized) {
         s->accum.release();
         s->accum2.release();
+        s->haveImage = false;
         s->haveVariance = false;
     }
+    // a block handed out by the device cache holds whatever its previous owner left in it: whenever the accumulators
+    // are (re)allocated there is no image to keep
+    float4 const *const before = s->accum.ptr;
     CB_CUDA(s->accum.reserve(npix));
-    if (variance)
+    if (s->accum.ptr != before)
+        s->haveImage = false;
+    if (variance) {
+        float4 const *const before2 = s->accum2.ptr;
         CB_CUDA(s->accum2.reserve(npix));
+        if (s->accum2.ptr != before2)
+            s->haveVariance = false;
+    }
     s->width = width;
     s->height = height;
     return CORNELIS_OK;
@@ -357,6 +369,25 @@ int applyAcceleration(cornelis_cuda_scene *s, int mode) {
 }
 
 } // namespace
+
+namespace cornelis_b200 {
+
+bool frameView(cornelis_cuda_scene *s, FrameView &out) {
+    if (!s || !s->accum.ptr || !s->width || !s->haveImage)
+        return false;
+    out.device = s->device;
+    out.stream = s->stream;
+    out.accum = s->accum.ptr;
+    out.accum2 = s->haveVariance ? s->accum2.ptr : nullptr;
+    out.npixels = static_cast<size_t>(s->width) * s->height;
+    out.haveVariance = s->haveVariance;
+    out.shape = &s->shape;
+    return true;
+}
+
+int failWith(cornelis_status code, const std::string &message) { return fail(code, message); }
+
+} // namespace cornelis_b200
 
 extern "C" {
 
@@ -545,6 +576,8 @@ int cornelis_cuda_render_accumulate(cornelis_cuda_scene *s, const cornelis_rende
     int32_t const sampleCount = p->sample_count > 0 ? p->sample_count : p->samples;
     if (p->first_sample < 0 || static_cast<int64_t>(p->first_sample) + sampleCount > (1 << 24))
         return fail(CORNELIS_ERR_INVALID_ARGUMENT, "sample range must lie in [0, 2^24)");
+    if (p->max_depth > 255)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "max_depth must be <= 255 (every path ends after 255 bounces)");
     uint64_t const npix64 = static_cast<uint64_t>(p->width) * static_cast<uint64_t>(p->height);
     if (npix64 > (1ull << 31))
         return fail(CORNELIS_ERR_INVALID_ARGUMENT, "frame too large");
@@ -582,11 +615,15 @@ int cornelis_cuda_render_accumulate(cornelis_cuda_scene *s, const cornelis_rende
 
     cudaStream_t st = s->stream;
     bool const keep = (p->flags & CORNELIS_RENDER_KEEP) != 0;
+    if (keep && !s->haveImage)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT,
+                    "KEEP needs a previous render of this frame size on this handle (the accumulators hold no image)");
     if (!keep) {
         CB_CUDA(cudaMemsetAsync(s->accum.ptr, 0, npix64 * sizeof(float4), st));
         if (variance)
             CB_CUDA(cudaMemsetAsync(s->accum2.ptr, 0, npix64 * sizeof(float4), st));
         s->haveVariance = variance;
+        s->haveImage = true;
     } else if (variance && !s->haveVariance) {
         return fail(CORNELIS_ERR_INVALID_ARGUMENT, "KEEP with VARIANCE needs a previous VARIANCE render");
     }
@@ -728,61 +765,10 @@ int cornelis_cuda_framebuffer_device(cornelis_cuda_scene *s, void **devicePtr, s
         return rc;
     if (!devicePtr || !nFloats)
         return fail(CORNELIS_ERR_INVALID_ARGUMENT, "null output pointer");
-    if (!s->accum.ptr || !s->width)
+    if (!s->accum.ptr || !s->width || !s->haveImage)
         return fail(CORNELIS_ERR_INVALID_ARGUMENT, "nothing has been rendered yet");
     *devicePtr = s->accum.ptr;
     *nFloats = static_cast<size_t>(s->width) * s->height * 4;
-    return CORNELIS_OK;
-}
-
-int cornelis_cuda_reduce_framebuffers(cornelis_cuda_scene *const *scenes, int n) {
-    if (!scenes || n <= 0 || !scenes[0])
-        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "no scenes to reduce");
-    cornelis_cuda_scene *root = scenes[0];
-    size_t const npix = static_cast<size_t>(root->width) * root->height;
-    if (!root->accum.ptr || !npix)
-        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "nothing has been rendered yet");
-    for (int k = 1; k < n; k++) {
-        cornelis_cuda_scene *peer = scenes[k];
-        if (!peer || peer->width != root->width || peer->height != root->height || !peer->accum.ptr ||
-            peer->haveVariance != root->haveVariance)
-            return fail(CORNELIS_ERR_INVALID_ARGUMENT, "scenes must hold renders of the same frame");
-        CB_CUDA(cudaSetDevice(peer->device));
-        CB_CUDA(cudaStreamSynchronize(peer->stream));
-    }
-    CB_CUDA(cudaSetDevice(root->device));
-    DeviceBuffer<float4> staging;
-    for (int k = 1; k < n; k++) {
-        cornelis_cuda_scene *peer = scenes[k];
-        int direct = peer->device == root->device;
-        if (!direct) {
-            CB_CUDA(cudaDeviceCanAccessPeer(&direct, root->device, peer->device));
-            if (direct) {
-                cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
-                if (e == cudaErrorPeerAccessAlreadyEnabled)
-                    cudaGetLastError();
-                else if (e != cudaSuccess)
-                    direct = 0;
-            }
-        }
-        const float4 *images[2] = {peer->accum.ptr, root->haveVariance ? peer->accum2.ptr : nullptr};
-        float4 *targets[2] = {root->accum.ptr, root->haveVariance ? root->accum2.ptr : nullptr};
-        for (int which = 0; which < 2; which++) {
-            if (!images[which])
-                continue;
-            const float4 *src = images[which];
-            if (!direct) {
-                CB_CUDA(staging.reserve(npix));
-                CB_CUDA(cudaMemcpyPeerAsync(staging.ptr, root->device, src, peer->device, npix * sizeof(float4),
-                                            root->stream));
-                src = staging.ptr;
-            }
-            launchAddImages(root->stream, root->shape, npix, targets[which], src);
-        }
-    }
-    CB_CUDA(cudaStreamSynchronize(root->stream));
-    CB_CUDA(cudaGetLastError());
-    staging.release();
     return CORNELIS_OK;
 }
 
@@ -791,7 +777,7 @@ int cornelis_cuda_resolve(cornelis_cuda_scene *s, int32_t samples, float *hostRg
         return rc;
     if (samples <= 0 || !hostRgb)
         return fail(CORNELIS_ERR_INVALID_ARGUMENT, "samples must be > 0 and host_rgb non-null");
-    if (!s->accum.ptr || !s->width)
+    if (!s->accum.ptr || !s->width || !s->haveImage)
         return fail(CORNELIS_ERR_INVALID_ARGUMENT, "nothing has been rendered yet");
     if (hostVariance && !s->haveVariance)
         return fail(CORNELIS_ERR_INVALID_ARGUMENT, "variance was not accumulated (CORNELIS_RENDER_VARIANCE)");
@@ -814,7 +800,7 @@ int cornelis_cuda_resolve_device(cornelis_cuda_scene *s, int32_t samples, void *
         return rc;
     if (samples <= 0 || !deviceRgb)
         return fail(CORNELIS_ERR_INVALID_ARGUMENT, "samples must be > 0 and device_rgb non-null");
-    if (!s->accum.ptr || !s->width)
+    if (!s->accum.ptr || !s->width || !s->haveImage)
         return fail(CORNELIS_ERR_INVALID_ARGUMENT, "nothing has been rendered yet");
     size_t const npix = static_cast<size_t>(s->width) * s->height;
     CB_CUDA(s->outRgb.reserve(3 * npix));
@@ -831,7 +817,7 @@ int cornelis_cuda_resolve_srgb8(cornelis_cuda_scene *s, int32_t samples, uint8_t
         return rc;
     if (samples <= 0 || !hostRgb8)
         return fail(CORNELIS_ERR_INVALID_ARGUMENT, "samples must be > 0 and host_rgb8 non-null");
-    if (!s->accum.ptr || !s->width)
+    if (!s->accum.ptr || !s->width || !s->haveImage)
         return fail(CORNELIS_ERR_INVALID_ARGUMENT, "nothing has been rendered yet");
     size_t const npix = static_cast<size_t>(s->width) * s->height;
     CB_CUDA(s->outRgb8.reserve(3 * npix));
@@ -949,6 +935,66 @@ int cornelis_cuda_intersect_device(cornelis_cuda_scene *s, size_t n, const void 
     return CORNELIS_OK;
 }
 
+int cornelis_cuda_intersect_compact(cornelis_cuda_scene *s, size_t n, const float *org, const float *dir,
+                                    uint32_t *hitQueue, uint32_t *nHits, uint32_t *missQueue, uint32_t *nMisses) {
+    if (int rc = checkScene(s))
+        return rc;
+    if (!org || !dir || !hitQueue || !nHits || !missQueue || !nMisses)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "null argument");
+    *nHits = *nMisses = 0;
+    if (n == 0)
+        return CORNELIS_OK;
+    if (n > (1u << 28))
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "batch too large");
+    // the pool as a render pass would hold these rays: origin, direction, throughput 1, radiance (1, 0, 0) | ray index
+    for (int a = 0; a < 4; a++)
+        CB_CUDA(s->pool[0][a].reserve(n));
+    CB_CUDA(s->hits.reserve(n));
+    CB_CUDA(s->hitQueue.reserve(n));
+    CB_CUDA(s->finished.reserve(2 * n));
+    CB_CUDA(s->control.reserve(1));
+    UPLOAD(s->stageF[0], org, 3 * n);
+    UPLOAD(s->stageF[1], dir, 3 * n);
+    launchPack4(s->stream, s->shape, n, s->stageF[0].ptr, s->pool[0][0].ptr);
+    launchPack4(s->stream, s->shape, n, s->stageF[1].ptr, s->pool[0][1].ptr);
+    std::vector<float4> state(n);
+    for (size_t k = 0; k < n; k++)
+        state[k] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    CB_CUDA(cudaMemcpyAsync(s->pool[0][2].ptr, state.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s->stream));
+    CB_CUDA(cudaStreamSynchronize(s->stream));
+    for (size_t k = 0; k < n; k++) {
+        uint32_t const index = static_cast<uint32_t>(k);
+        float w;
+        std::memcpy(&w, &index, sizeof w);
+        state[k] = make_float4(1.0f, 0.0f, 0.0f, w);
+    }
+    CB_CUDA(cudaMemcpyAsync(s->pool[0][3].ptr, state.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s->stream));
+    Control init{};
+    init.nIn = static_cast<uint32_t>(n);
+    *s->hostControl = init;
+    CB_CUDA(cudaMemcpyAsync(s->control.ptr, s->hostControl, sizeof(Control), cudaMemcpyHostToDevice, s->stream));
+    launchIntersect(s->stream, s->shape, s->control.ptr, s->view, poolView(s, 0), s->hits.ptr, s->hitQueue.ptr,
+                    s->finished.ptr);
+    CB_CUDA(cudaMemcpyAsync(s->hostControl, s->control.ptr, sizeof(Control), cudaMemcpyDeviceToHost, s->stream));
+    CB_CUDA(cudaStreamSynchronize(s->stream));
+    CB_CUDA(cudaGetLastError());
+    uint32_t const hitCount = s->hostControl->nHit, missCount = s->hostControl->nFinished;
+    if (hitCount > n || missCount > n)
+        return fail(CORNELIS_ERR_CUDA, "queue tails exceed the batch");
+    if (hitCount)
+        CB_CUDA(cudaMemcpyAsync(hitQueue, s->hitQueue.ptr, hitCount * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    std::vector<FinishedPath> done(missCount);
+    if (missCount)
+        CB_CUDA(cudaMemcpyAsync(done.data(), s->finished.ptr, missCount * sizeof(FinishedPath), cudaMemcpyDeviceToHost,
+                                s->stream));
+    CB_CUDA(cudaStreamSynchronize(s->stream));
+    for (uint32_t k = 0; k < missCount; k++)
+        missQueue[k] = done[k].pixel;
+    *nHits = hitCount;
+    *nMisses = missCount;
+    return CORNELIS_OK;
+}
+
 static int checkMaterialIds(cornelis_cuda_scene *s, size_t n, const int32_t *mat) {
     for (size_t k = 0; k < n; k++)
         if (mat[k] < 0 || static_cast<uint32_t>(mat[k]) >= s->view.nMaterials)
@@ -1060,6 +1106,21 @@ int cornelis_cuda_rng_uniforms(cornelis_cuda_scene *s, uint64_t seed, size_t n, 
               reinterpret_cast<const uint32_t *>(a.ptr), reinterpret_cast<const uint32_t *>(b.ptr),
               reinterpret_cast<const uint32_t *>(c.ptr), s->stageF[0].ptr);
     DOWNLOAD(out, s->stageF[0], 4 * n);
+    CB_CUDA(cudaStreamSynchronize(s->stream));
+    CB_CUDA(cudaGetLastError());
+    return CORNELIS_OK;
+}
+
+int cornelis_cuda_selftest_srgb8(cornelis_cuda_scene *s, uint32_t firstBits, size_t n, uint8_t *hostOut) {
+    if (int rc = checkScene(s))
+        return rc;
+    if (!hostOut)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "host_out is null");
+    if (n == 0)
+        return CORNELIS_OK;
+    CB_CUDA(s->outRgb8.reserve(n));
+    launchSrgb8Sweep(s->stream, s->shape, firstBits, n, s->outRgb8.ptr);
+    CB_CUDA(cudaMemcpyAsync(hostOut, s->outRgb8.ptr, n, cudaMemcpyDeviceToHost, s->stream));
     CB_CUDA(cudaStreamSynchronize(s->stream));
     CB_CUDA(cudaGetLastError());
     return CORNELIS_OK;

@@ -144,6 +144,13 @@ __device__ __forceinline__ AppendSlots blockAppend2(bool flagA, bool flagB, uint
 
 // ----------------------------------------------------------------------------------------------- path packing --
 
+// Path length limit.  The depth travels in 8 bits next to the sample index and selects the Philox block of a bounce, so
+// a path is ended when it reaches 255 bounces.  Finite paths never get there (Russian roulette lets a path survive a
+// bounce with probability <= 0.5445 from depth 3 on, Render.cpp:153-165: 255 bounces have probability < 1e-66); the
+// paths that do are those whose throughput became NaN (the reference's Oren-Nayar quirk, about one in 1e8 samples):
+// `prob < u` is then false for ever (Render.cpp:189) and in a closed scene the reference's loop would never end.
+constexpr uint32_t kDepthLimit = 255u;
+
 __device__ __forceinline__ uint32_t packSampleDepth(uint32_t sample, uint32_t depth) {
     return (sample << 8) | (depth > 255u ? 255u : depth);
 }

@@ -152,9 +152,9 @@ __global__ void __launch_bounds__(kPersistentThreads, CORNELIS_PERSISTENT_MIN_BL
                     shadeBounce(sh.materials[material], P, N, depth, uniformFromBits(r.v[0]), uniformFromBits(r.v[1]),
                                 uniformFromBits(r.v[2]), uniformFromBits(r.v[3]), org, dir, thr, rad);
                 shaded++;
-                depth = depth < 255u ? depth + 1u : 255u;
+                depth += 1u; // <= kDepthLimit: a path that reaches it ends below
                 deepest = depth > deepest ? depth : deepest;
-                finished = !survives || (cfg.maxDepth && depth >= cfg.maxDepth);
+                finished = !survives || (cfg.maxDepth && depth >= cfg.maxDepth) || depth >= kDepthLimit;
             }
         }
         // ---- per-pixel accumulation (Render.cpp:245-248) ----
@@ -321,9 +321,9 @@ __global__ void __launch_bounds__(kPersistentThreads, CORNELIS_PERSISTENT_MIN_BL
                     shadeRoulette(sh.materials[material], depth, uniformFromBits(r.v[0]), thr, rad, prob);
                 x0 = uniformFromBits(r.v[1]), x1 = uniformFromBits(r.v[2]), x2 = uniformFromBits(r.v[3]);
                 shaded++;
-                depth = depth < 255u ? depth + 1u : 255u;
+                depth += 1u; // <= kDepthLimit: a path that reaches it ends below
                 deepest = depth > deepest ? depth : deepest;
-                finished = !survives || (cfg.maxDepth && depth >= cfg.maxDepth);
+                finished = !survives || (cfg.maxDepth && depth >= cfg.maxDepth) || depth >= kDepthLimit;
                 park = !finished;
             }
         }
@@ -385,9 +385,9 @@ static cudaError_t configureOne(LaunchShape &shape, int &grid) {
     shape.persistentQueueOffset = static_cast<uint32_t>(queueOffset);
     auto kernel = shape.persistentQueued ? reinterpret_cast<const void *>(k_persistent_queued<kGrid>)
                                          : reinterpret_cast<const void *>(k_persistent<kGrid>);
-    if (shape.persistentSmemBytes > 48 * 1024)
+    if (shape.smemOptin > 48 * 1024) // per function and device, not per scene: always the device's limit
         if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(shape.persistentSmemBytes))) != cudaSuccess)
+                                      static_cast<int>(shape.smemOptin))) != cudaSuccess)
             return e;
     if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared)) != cudaSuccess)

@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_SHADE_MIN_BLOCKS) k_sh
                                 uniformFromBits(r.v[2]), uniformFromBits(r.v[3]), org, dir, thr, rad);
             depth += 1;
             deepest = depth > deepest ? depth : deepest;
-            if (cfg.maxDepth && depth >= cfg.maxDepth)
+            if ((cfg.maxDepth && depth >= cfg.maxDepth) || depth >= kDepthLimit)
                 alive = false;
             finish = !alive && (rad.r != 0.0f || rad.g != 0.0f || rad.b != 0.0f);
         }
@@ -374,6 +374,14 @@ __global__ void __launch_bounds__(kBlockThreads) k_resolve_srgb8(uint32_t npixel
         rgb8[3 * p + 1] = srgb8(s.y * invSamples);
         rgb8[3 * p + 2] = srgb8(s.z * invSamples);
     }
+}
+
+// The display transform of k_resolve_srgb8 over consecutive float bit patterns: out[i] = srgb8(float with bits first + i).
+// 2^30 + 1 patterns cover every float in [0, 1] (tests/test_gpu_parity.py compares all of them with the oracle).
+__global__ void __launch_bounds__(kBlockThreads) k_srgb8_sweep(uint32_t first, size_t n, uint8_t *__restrict__ out) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        out[i] = srgb8(__uint_as_float(first + static_cast<uint32_t>(i)));
 }
 
 // dst += src over float4 images; src may live on a peer GPU (NVLink peer access): the loads go over the link, the
@@ -657,6 +665,10 @@ void launchResolveSrgb8(cudaStream_t s, const LaunchShape &shape, uint32_t npixe
     k_resolve_srgb8<<<gridFor(npixels, shape.numSMs, 8), kBlockThreads, 0, s>>>(npixels, inv, accum, rgb8);
 }
 
+void launchSrgb8Sweep(cudaStream_t s, const LaunchShape &shape, uint32_t first, size_t n, uint8_t *out) {
+    k_srgb8_sweep<<<gridFor(n, shape.numSMs, 8), kBlockThreads, 0, s>>>(first, n, out);
+}
+
 void launchAddImages(cudaStream_t s, const LaunchShape &shape, size_t n4, float4 *dst, const float4 *src) {
     k_add_images<<<gridFor(n4, shape.numSMs, 8), kBlockThreads, 0, s>>>(n4, dst, src);
 }
@@ -732,37 +744,26 @@ void launchUnpackHits(cudaStream_t s, const LaunchShape &shape, size_t n, const 
 
 cudaError_t configureKernels(LaunchShape &shape) {
     cudaError_t e;
-    int const bytes = static_cast<int>(shape.sceneSmemBytes);
-    // Scenes whose tables exceed the default 48 KB of dynamic shared memory opt in to the large carve-out.
-    if (shape.sceneSmemBytes > 48 * 1024) {
-        if ((e = cudaFuncSetAttribute(k_intersect<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
-            return e;
-        if ((e = cudaFuncSetAttribute(k_intersect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
-            return e;
-        if ((e = cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
-            return e;
-        if ((e = cudaFuncSetAttribute(k_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
-            return e;
-        if ((e = cudaFuncSetAttribute(k_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
-            return e;
-        if ((e = cudaFuncSetAttribute(k_intersect_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
-            return e;
-        if ((e = cudaFuncSetAttribute(k_intersect_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
-            return e;
-        if ((e = cudaFuncSetAttribute(k_hit_surface<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
-            return e;
-        if ((e = cudaFuncSetAttribute(k_hit_surface<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess)
-            return e;
-    }
-    {   // the batch kernel may add a paired copy of the sphere table (launchIntersectBatch)
-        size_t const most = shape.smemOptin;
-        if (most > 48 * 1024)
-            if ((e = cudaFuncSetAttribute(k_intersect_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(most))) != cudaSuccess)
+    // Every kernel that stages the scene opts in to the device's largest dynamic shared-memory size once.  The attribute
+    // is per function and per device, not per scene: sizing it from one scene's tables would lower the limit under
+    // another live scene whose tables are larger.
+    if (shape.smemOptin > 48 * 1024) {
+        int const most = static_cast<int>(shape.smemOptin);
+        const void *staging[] = {reinterpret_cast<const void *>(k_intersect<false>),
+                                 reinterpret_cast<const void *>(k_intersect<true>),
+                                 reinterpret_cast<const void *>(k_walk),
+                                 reinterpret_cast<const void *>(k_shade<false>),
+                                 reinterpret_cast<const void *>(k_shade<true>),
+                                 reinterpret_cast<const void *>(k_intersect_batch<false>),
+                                 reinterpret_cast<const void *>(k_intersect_batch<true>),
+                                 reinterpret_cast<const void *>(k_hit_surface<false>),
+                                 reinterpret_cast<const void *>(k_hit_surface<true>)};
+        for (const void *kernel : staging)
+            if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, most)) != cudaSuccess)
                 return e;
-        if (const char *env = std::getenv("CORNELIS_BATCH_PACKED"))
-            shape.batchPacked = std::atoi(env) != 0;
     }
+    if (const char *env = std::getenv("CORNELIS_BATCH_PACKED"))
+        shape.batchPacked = std::atoi(env) != 0;
     auto resident = [&](auto kernel, size_t smem, int &grid) -> cudaError_t {
         int blocks = 0;
         cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, kBlockThreads, smem);

@@ -50,6 +50,7 @@ void launchResolve(cudaStream_t s, const LaunchShape &shape, uint32_t npixels, u
 void launchResolveSrgb8(cudaStream_t s, const LaunchShape &shape, uint32_t npixels, uint32_t samples,
                         const float4 *accum, uint8_t *rgb8);
 
+void launchSrgb8Sweep(cudaStream_t s, const LaunchShape &shape, uint32_t first, size_t n, uint8_t *out);
 void launchAddImages(cudaStream_t s, const LaunchShape &shape, size_t n4, float4 *dst, const float4 *src);
 
 void launchPixelRays(cudaStream_t s, const LaunchShape &shape, const DevCamera &cam, uint32_t n, float dx, float dy,

@@ -2,6 +2,7 @@
 // 4096 spp, and writes cornelisrender2.png, as the reference binary does.  The reference ignores argv; the flags
 // below expose what it hard-codes.
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -124,6 +125,7 @@ static void usage() {
               "                [--devices G] [--pool P] [--output file.png] [--no-save] [--drop-nonfinite] [--quiet]\n"
               "                [--scene cornell|spheres] [--spheres N] [--accel auto|none|grid]\n"
               "                [--progressive] [--time-budget SECONDS]   (spp is then the upper limit)\n"
+              "                [--dump-raw file.f32]   (the float frame buffer: height*width*3 floats, row-major)\n"
               "defaults reproduce the reference CLI: the Cornell box, 512x512, 4096 spp, cornelisrender2.png");
 }
 
@@ -134,6 +136,7 @@ int main(int argc, char *argv[]) {
     bool quiet = false;
     std::string sceneName = "cornell";
     std::size_t sphereCount = 10000;
+    std::string rawPath;
     for (int i = 1; i < argc; i++) {
         std::string const a = argv[i];
         auto next = [&]() -> char const * {
@@ -157,6 +160,7 @@ int main(int argc, char *argv[]) {
         else if (a == "--quiet") quiet = true;
         else if (a == "--progressive") options.progressive = true;
         else if (a == "--time-budget") options.timeBudgetSeconds = std::atof(next());
+        else if (a == "--dump-raw") rawPath = next();
         else if (a == "--scene") sceneName = next();
         else if (a == "--spheres") sphereCount = static_cast<std::size_t>(std::atoll(next()));
         else if (a == "--accel") {
@@ -191,6 +195,27 @@ int main(int argc, char *argv[]) {
         });
         double const wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         auto const &st = session.statistics();
+        // Non-finite pixels: the reference's Oren-Nayar term is NaN when |w.z| rounds above 1 (about once per 1e8
+        // samples) and the pixel then stays NaN; it is kept unless --drop-nonfinite.  In the PNG such a pixel is black:
+        // std::clamp passes NaN through and the conversion to 8 bits gives 0 (formally undefined in C++; x86's cvttsd2si
+        // and the device's cvt both yield 0, and so does the reference's binary).
+        std::size_t nonFinite = 0;
+        for (auto const &px : session.frameBuffer())
+            if (!std::isfinite(px(0)) || !std::isfinite(px(1)) || !std::isfinite(px(2)))
+                nonFinite++;
+        if (!rawPath.empty()) {
+            std::FILE *f = std::fopen(rawPath.c_str(), "wb");
+            auto const &fb = session.frameBuffer();
+            std::size_t const n = static_cast<std::size_t>(fb.width()) * static_cast<std::size_t>(fb.height());
+            if (!f || std::fwrite(fb.data(), 3 * sizeof(float), n, f) != n) {
+                std::fprintf(stderr, "cornelis: cannot write %s\n", rawPath.c_str());
+                return 1;
+            }
+            std::fclose(f);
+        }
+        if (!quiet && nonFinite)
+            std::printf("%zu non-finite pixel(s) (kept as the reference keeps them; black in the PNG; --drop-nonfinite "
+                        "skips the offending paths)\n", nonFinite);
         if (!quiet)
             std::printf("%dx%d, %d spp, %d device(s): %.3f s wall, %.3f s on the GPU, %.1f Msamples/s, %.1f Mrays/s, "
                         "%.3f rays/sample, deepest path %u%s%s\n",

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CORNELIS_CUDA_ABI_VERSION 1
+#define CORNELIS_CUDA_ABI_VERSION 2
 
 typedef enum cornelis_status {
     CORNELIS_OK = 0,
@@ -34,7 +34,8 @@ typedef enum cornelis_status {
     CORNELIS_ERR_NO_DEVICE = 2,        /* no CUDA device / driver: the product has no CPU path */
     CORNELIS_ERR_CUDA = 3,             /* a CUDA runtime call failed; see cornelis_cuda_last_error() */
     CORNELIS_ERR_OUT_OF_MEMORY = 4,
-    CORNELIS_ERR_ABORTED = 5           /* the progress callback asked to stop (RenderCommand::Abort, Render.hpp:10-14) */
+    CORNELIS_ERR_ABORTED = 5,          /* the progress callback asked to stop (RenderCommand::Abort, Render.hpp:10-14) */
+    CORNELIS_ERR_NCCL = 6              /* libnccl.so.2 could not be loaded, or an NCCL call failed */
 } cornelis_status;
 
 /* ---- scene description PODs: field-for-field the reference's SceneDescription.hpp:14-53 ---------------------- */
@@ -93,7 +94,9 @@ typedef struct cornelis_render_params {
     int32_t samples;         /* RenderOptions::samplesAA of the whole image: the resolve divides by it */
     int32_t first_sample;    /* this call renders global sample indices [first_sample, first_sample + sample_count) */
     int32_t sample_count;    /*   of every pixel — the unit of multi-GPU sharding; 0 = all `samples` */
-    int32_t max_depth;       /* <= 0: unlimited, as the reference (Render.cpp:237); else paths stop after this many bounces */
+    int32_t max_depth;       /* <= 0: no cap, as the reference (Render.cpp:237); else paths stop after this many bounces
+                                (<= 255).  Without a cap a path still ends at 255 bounces: only paths whose throughput
+                                became NaN get there, and in a closed scene they would otherwise never end */
     uint64_t seed;           /* PRNG::DefaultSeed = 19791102 (PRNG.hpp:12) */
     uint32_t flags;          /* CORNELIS_RENDER_* */
     int32_t pipeline;        /* CORNELIS_PIPELINE_* */
@@ -161,14 +164,44 @@ int cornelis_cuda_scene_acceleration(cornelis_cuda_scene *scene, int *grid_enabl
 int cornelis_cuda_render_accumulate(cornelis_cuda_scene *scene, const cornelis_render_params *params,
                                     cornelis_progress_fn progress, void *progress_user, cornelis_render_stats *stats);
 
-/* Device pointer of the accumulation buffer: width*height float4 (sum r, g, b, sample count), for the cross-GPU sum
- * (one all-reduce of n_floats floats).  Valid until the next render with a different frame size or scene destroy. */
+/* Device pointer of the accumulation buffer: width*height float4 (sum r, g, b, and in .w the number of finished paths
+ * that CONTRIBUTED, i.e. ended with non-zero radiance — not the sample count: the resolve divides by `samples`).
+ * Valid until the next render with a different frame size or scene destroy. */
 int cornelis_cuda_framebuffer_device(cornelis_cuda_scene *scene, void **device_ptr, size_t *n_floats);
 
-/* Multi-GPU, one process: sum the accumulation buffers of n scenes (one per GPU of this box, same frame size) into
- * scenes[0].  GPU 0 reads its peers' buffers directly over NVLink (peer access) inside one kernel per peer; without
- * peer access the buffers are staged through cudaMemcpyPeer.  (bench.py, one process per GPU, uses an NCCL
- * all-reduce on cornelis_cuda_framebuffer_device() instead.) */
+/* ---- multi-GPU: the one exchange step of the path ----------------------------------------------------------------
+ *
+ * The estimator is a plain mean over samples (Render.cpp:245-250) and the device random numbers are keyed by the
+ * GLOBAL sample index, so GPU g of G renders sample indices [g*spp/G, (g+1)*spp/G) of every pixel into its own
+ * accumulators and the accumulators are summed ONCE: one ncclAllReduce (or ncclReduce) of width*height*4 floats per
+ * GPU over NVLink; cornelis_cuda_resolve then applies 1/samples.  NCCL (libnccl.so.2) is loaded on first use —
+ * the copy already in the process if there is one (e.g. torch's), else the system's — and its absence is an error
+ * (CORNELIS_ERR_NCCL), not a fallback.  A communicator is either
+ *   - all GPUs of one process: cornelis_cuda_comm_init_all (ncclCommInitAll), one scene handle per device, or
+ *   - one rank of a one-process-per-GPU job: rank 0 calls cornelis_cuda_comm_unique_id, hands the 128 bytes to the
+ *     other ranks by whatever means the job has (bench.py: torch.distributed), every rank calls
+ *     cornelis_cuda_comm_init_rank (ncclCommInitRank).  */
+typedef struct cornelis_cuda_comm cornelis_cuda_comm;
+#define CORNELIS_COMM_ID_BYTES 128
+
+int cornelis_cuda_comm_unique_id(uint8_t id[CORNELIS_COMM_ID_BYTES]);
+int cornelis_cuda_comm_init_rank(const uint8_t id[CORNELIS_COMM_ID_BYTES], int rank, int n_ranks, int device,
+                                 cornelis_cuda_comm **out_comm);
+int cornelis_cuda_comm_init_all(const int *devices, int n_devices, cornelis_cuda_comm **out_comm);
+int cornelis_cuda_comm_destroy(cornelis_cuda_comm *comm);
+/* n_ranks of the communicator, how many of them live in this process, and NCCL's version code.  Outputs may be NULL. */
+int cornelis_cuda_comm_info(cornelis_cuda_comm *comm, int *n_ranks, int *n_local, int *nccl_version);
+
+/* In-place sum of the accumulation images (and of the second-moment images after CORNELIS_RENDER_VARIANCE renders) of
+ * all ranks: afterwards every rank holds the image of all samples.  `scenes` are this process's handles in the
+ * communicator's device order (n_local = 1 for a per-rank communicator); all must hold renders of the same frame.
+ * One grouped ncclAllReduce, enqueued on each scene's stream: later calls on a scene are ordered behind it. */
+int cornelis_cuda_allreduce_framebuffers(cornelis_cuda_comm *comm, cornelis_cuda_scene *const *scenes, int n_local);
+
+/* One process, several GPUs: sum the accumulation images of n scenes into scenes[0] and wait for it.  Scenes on
+ * distinct GPUs are summed by one grouped ncclReduce (root = scenes[0]'s device) over a process-wide communicator
+ * that is created for that device set on first use and kept; scenes that share a GPU with an earlier one are first
+ * added to it locally (no exchange to make).  RenderSession with RenderOptions::devices > 1 calls this. */
 int cornelis_cuda_reduce_framebuffers(cornelis_cuda_scene *const *scenes, int n);
 
 /* color = sum * (1.0f / samples) (Render.cpp:250) and download: host_rgb[3*W*H]; host_variance[3*W*H] optional
@@ -202,6 +235,15 @@ int cornelis_cuda_intersect(cornelis_cuda_scene *scene, size_t n, const float *o
 int cornelis_cuda_intersect_device(cornelis_cuda_scene *scene, size_t n, const void *d_org4, const void *d_dir4,
                                    void *d_hit2, int repeats, float *ms_per_launch);
 
+/* The intersect stage of ONE wavefront pass on an explicit ray batch, compaction included (Render.cpp:110-150): the
+ * rays are placed in the path pool as the render loop would hold them, the pass's own kernels run (k_intersect, or
+ * k_walk + k_compact_hits for grid scenes), and the queues come back: hit_queue[0 .. *n_hits) are the indices of the
+ * rays with t < INF — the reference's rebuilt activeList (Render.cpp:142-149), in no particular order — and
+ * miss_queue[0 .. *n_misses) the indices of the rays that left the list (every ray of the batch carries non-zero
+ * radiance, so each miss reaches the finished queue).  Both arrays must hold n entries. */
+int cornelis_cuda_intersect_compact(cornelis_cuda_scene *scene, size_t n, const float *org, const float *dir,
+                                    uint32_t *hit_queue, uint32_t *n_hits, uint32_t *miss_queue, uint32_t *n_misses);
+
 /* LayeredBRDF::generateDirection / operator() / pdf (Materials.hpp:255-293) on explicit inputs. */
 int cornelis_cuda_bsdf_sample(cornelis_cuda_scene *scene, size_t n, const int32_t *mat, const float *wo,
                               const float *N, const float *x, float *wi, float *pdf, float *f);
@@ -226,6 +268,10 @@ int cornelis_cuda_rng_uniforms(cornelis_cuda_scene *scene, uint64_t seed, size_t
  * mode 2 the (sqrt, reciprocal) pair of normalize over float bit patterns 0..n-1 — n = 2^32 checks EVERY float.
  * *mismatches receives the number of results whose bits differ. */
 int cornelis_cuda_selftest_arith(cornelis_cuda_scene *scene, int mode, uint64_t n, uint32_t seed, uint64_t *mismatches);
+
+/* Device self-test of the display transform + 8-bit quantisation of cornelis_cuda_resolve_srgb8 (Color.cpp:64-80,
+ * FrameBuffer.hpp:91-95) over consecutive float bit patterns: host_out[i] = srgb8(float whose bits are first_bits + i). */
+int cornelis_cuda_selftest_srgb8(cornelis_cuda_scene *scene, uint32_t first_bits, size_t n, uint8_t *host_out);
 
 #ifdef __cplusplus
 }

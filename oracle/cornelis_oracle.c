@@ -729,6 +729,7 @@ typedef struct {
     Rect *tiles;
     Xoshiro128Plus *tileRng;
     float *mean, *variance;
+    int32_t stride, outW; /* stride > 1: pixel (i, j) is stored at (j / stride) * outW + i / stride (ora_render_strided) */
     atomic_llong rays;
     atomic_int maxDepth;
 } RenderCtx;
@@ -791,6 +792,8 @@ static void renderTiles(void *vctx, int64_t lo, int64_t hi) {
                     color = add(color, rad[k]);
                 color = scale(color, 1.0f / spp);
                 int64_t pix = (int64_t)j * c->W + i; /* FrameBuffer.hpp:66 */
+                if (c->stride > 1)
+                    pix = (int64_t)(j / c->stride) * c->outW + i / c->stride;
                 st3(c->mean, pix, color);
                 if (c->variance) {
                     for (int ch = 0; ch < 3; ch++) {
@@ -833,6 +836,8 @@ int ora_render(const ora_scene *s, int32_t W, int32_t H, int32_t spp, int32_t ti
     c.spp = spp;
     c.mean = mean;
     c.variance = variance;
+    c.stride = 1;
+    c.outW = W;
     atomic_init(&c.rays, 0);
     atomic_init(&c.maxDepth, 0);
     c.tiles = (Rect *)malloc(sizeof(Rect) * (size_t)nTiles);
@@ -854,6 +859,52 @@ int ora_render(const ora_scene *s, int32_t W, int32_t H, int32_t spp, int32_t ti
         stats[0] = (double)atomic_load(&c.rays);
         stats[1] = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
         stats[2] = (double)W * H * spp;
+        stats[3] = atomic_load(&c.maxDepth);
+    }
+    free(c.tiles);
+    free(c.tileRng);
+    return 0;
+}
+
+/* Every stride-th pixel of the W x H frame in each dimension, each as its own 1 x 1 tile (its generator is the root
+ * jumped k times, k its index in the strided image): the integrand of a full-size frame at a fraction of the cost. */
+int ora_render_strided(const ora_scene *s, int32_t W, int32_t H, int32_t spp, int32_t stride, uint64_t seed,
+                       int32_t nthreads, float *mean, float *variance, double *stats) {
+    if (spp <= 0 || W <= 0 || H <= 0 || stride <= 0)
+        return 1;
+    int32_t const outW = (W + stride - 1) / stride, outH = (H + stride - 1) / stride;
+    int32_t const nTiles = outW * outH;
+    RenderCtx c;
+    c.s = s;
+    c.W = W;
+    c.H = H;
+    c.spp = spp;
+    c.mean = mean;
+    c.variance = variance;
+    c.stride = stride;
+    c.outW = outW;
+    atomic_init(&c.rays, 0);
+    atomic_init(&c.maxDepth, 0);
+    c.tiles = (Rect *)malloc(sizeof(Rect) * (size_t)nTiles);
+    c.tileRng = (Xoshiro128Plus *)malloc(sizeof(Xoshiro128Plus) * (size_t)nTiles);
+    Xoshiro128Plus g;
+    prng_seed(&g, seed);
+    for (int32_t k = 0; k < nTiles; k++) {
+        int32_t const i = (k % outW) * stride, j = (k / outW) * stride;
+        c.tiles[k] = mkRect(i, j, i, j);
+        c.tileRng[k] = g;
+        prng_jump(&g);
+    }
+    /* a stride of 1 stores through the full-frame index, like ora_render */
+    memset(mean, 0, sizeof(float) * 3u * (size_t)outW * (size_t)outH);
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    parallelFor(nTiles, 16, nthreads, renderTiles, &c);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (stats) {
+        stats[0] = (double)atomic_load(&c.rays);
+        stats[1] = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+        stats[2] = (double)outW * outH * spp;
         stats[3] = atomic_load(&c.maxDepth);
     }
     free(c.tiles);

@@ -78,6 +78,9 @@ class Oracle:
         lib.ora_render.restype = C.c_int
         lib.ora_render.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64,
                                    C.c_int32, _f32p, C.c_void_p, C.c_void_p]
+        lib.ora_render_strided.restype = C.c_int
+        lib.ora_render_strided.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64,
+                                           C.c_int32, _f32p, C.c_void_p, C.c_void_p]
         lib.ora_to_srgb8.argtypes = [C.c_int64, _f32p, _u8p]
         lib.ora_frame_tiling.restype = C.c_int32
         lib.ora_frame_tiling.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
@@ -228,6 +231,25 @@ class OracleScene:
                                         st.ctypes.data_as(C.c_void_p) if stats else None)
         if rc != 0:
             raise RuntimeError(f"ora_render failed rc={rc}")
+        out = dict(mean=mean)
+        if variance:
+            out["variance"] = var
+        if stats:
+            out["stats"] = dict(rays=st[0], seconds=st[1], pixel_samples=st[2], max_depth=int(st[3]))
+        return out
+
+
+    def render_strided(self, W, H, spp, stride, seed=19791102, threads=0, variance=False, stats=False):
+        """Every stride-th pixel (both dimensions) of the W x H frame, integrated as in the full frame."""
+        ow, oh = -(-W // stride), -(-H // stride)
+        mean = np.zeros((oh, ow, 3), np.float32)
+        var = np.zeros((oh, ow, 3), np.float32) if variance else None
+        st = np.zeros(4, np.float64) if stats else None
+        rc = self.oracle.lib.ora_render_strided(self.handle, W, H, spp, stride, seed, threads, mean,
+                                                var.ctypes.data_as(C.c_void_p) if variance else None,
+                                                st.ctypes.data_as(C.c_void_p) if stats else None)
+        if rc != 0:
+            raise RuntimeError(f"ora_render_strided failed rc={rc}")
         out = dict(mean=mean)
         if variance:
             out["variance"] = var

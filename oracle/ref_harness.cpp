@@ -292,19 +292,15 @@ void ora_prng_floats(uint64_t seed, int64_t jumps, int64_t n, float *out) {
         out[k] = g();
 }
 
-int ora_render(const ora_scene *scene, int32_t W, int32_t H, int32_t spp, int32_t tileW, int32_t tileH,
-               uint64_t seed, int32_t nthreads, float *mean, float *variance, double *stats) {
-    if (spp <= 0 || W <= 0 || H <= 0)
-        return 1;
+// The tile loop of RenderSession::render (Render.cpp:327-343) over an arbitrary list of tiles.  `stride` > 1 stores
+// pixel (i, j) at (j / stride) * outW + i / stride of the output arrays (ora_render_strided).
+static int renderTiles(const ora_scene *scene, int32_t W, int32_t H, int32_t spp, std::vector<TileInfo> &tiles,
+                       int32_t stride, int32_t outW, int32_t outH, int32_t nthreads, float *mean, float *variance,
+                       double *stats) {
     SceneData &sd = scene->data;
     RenderOptions options{spp}; // samplesAA is a const member (RenderOptions.hpp:15): aggregate-initialise
     RGBFrameBuffer fb(PixelRect(W, H));
-    PRNG rootRng(seed);
-
-    // Render.cpp:327-331
-    FrameTiling tiling(PixelRect(fb.width(), fb.height()), PixelRect{tileW, tileH});
-    for (auto &tileInfo : tiling)
-        tileInfo.randomGen = cloneForThread(rootRng, tileInfo.tileNumber);
+    auto outIndex = [&](int64_t i, int64_t j) { return stride > 1 ? (j / stride) * outW + i / stride : j * W + i; };
 
     bool const instrumented = variance != nullptr || stats != nullptr;
     std::atomic<int64_t> raysTraced{0};
@@ -314,7 +310,7 @@ int ora_render(const ora_scene *scene, int32_t W, int32_t H, int32_t spp, int32_
     auto const t0 = std::chrono::steady_clock::now();
     tbb::task_group group;
     group.run_and_wait([&] {
-        tbb::parallel_for_each(std::begin(tiling), std::end(tiling), [&](TileInfo &tileInfo) {
+        tbb::parallel_for_each(std::begin(tiles), std::end(tiles), [&](TileInfo &tileInfo) {
             if (!instrumented) {
                 integrateTile(tileInfo, options, sd, fb); // Render.cpp:343
                 return;
@@ -352,8 +348,7 @@ int ora_render(const ora_scene *scene, int32_t W, int32_t H, int32_t spp, int32_
                             double q = 0.0;
                             for (auto const &term : L)
                                 q += (term(c) - mu) * (term(c) - mu);
-                            variance[3 * (static_cast<int64_t>(j) * W + i) + c] =
-                                spp > 1 ? static_cast<float>(q / (spp - 1)) : 0.0f;
+                            variance[3 * outIndex(i, j) + c] = spp > 1 ? static_cast<float>(q / (spp - 1)) : 0.0f;
                         }
                     }
                 }
@@ -367,15 +362,55 @@ int ora_render(const ora_scene *scene, int32_t W, int32_t H, int32_t spp, int32_
     auto const t1 = std::chrono::steady_clock::now();
     tbb::shim::requestedThreads().store(0);
 
-    for (int64_t k = 0; k < static_cast<int64_t>(W) * H; k++)
-        store3(mean, k, fb.data()[k]);
+    if (stride > 1) {
+        for (int64_t j = 0; j < H; j += stride)
+            for (int64_t i = 0; i < W; i += stride)
+                store3(mean, outIndex(i, j), fb.data()[j * W + i]);
+    } else {
+        for (int64_t k = 0; k < static_cast<int64_t>(W) * H; k++)
+            store3(mean, k, fb.data()[k]);
+    }
     if (stats) {
         stats[0] = static_cast<double>(raysTraced.load());
         stats[1] = std::chrono::duration<double>(t1 - t0).count();
-        stats[2] = static_cast<double>(W) * H * spp;
+        stats[2] = static_cast<double>(outW) * outH * spp;
         stats[3] = maxDepth.load();
     }
     return 0;
+}
+
+int ora_render(const ora_scene *scene, int32_t W, int32_t H, int32_t spp, int32_t tileW, int32_t tileH,
+               uint64_t seed, int32_t nthreads, float *mean, float *variance, double *stats) {
+    if (spp <= 0 || W <= 0 || H <= 0)
+        return 1;
+    PRNG rootRng(seed);
+    // Render.cpp:327-331
+    FrameTiling tiling(PixelRect(W, H), PixelRect{tileW, tileH});
+    std::vector<TileInfo> tiles(std::begin(tiling), std::end(tiling));
+    for (auto &tileInfo : tiles)
+        tileInfo.randomGen = cloneForThread(rootRng, tileInfo.tileNumber);
+    return renderTiles(scene, W, H, spp, tiles, 1, W, H, nthreads, mean, variance, stats);
+}
+
+int ora_render_strided(const ora_scene *scene, int32_t W, int32_t H, int32_t spp, int32_t stride, uint64_t seed,
+                       int32_t nthreads, float *mean, float *variance, double *stats) {
+    if (spp <= 0 || W <= 0 || H <= 0 || stride <= 0)
+        return 1;
+    int32_t const outW = (W + stride - 1) / stride, outH = (H + stride - 1) / stride;
+    // one 1 x 1 tile per strided pixel; generators as Render.cpp:329-331 hands them to tiles: the root jumped k times
+    // (incrementally here: cloneForThread(root, k) costs k jumps)
+    PRNG g(seed);
+    std::vector<TileInfo> tiles;
+    tiles.reserve(static_cast<std::size_t>(outW) * outH);
+    for (int32_t k = 0; k < outW * outH; k++) {
+        int32_t const i = (k % outW) * stride, j = (k / outW) * stride;
+        TileInfo t(static_cast<std::size_t>(k), PixelRect(PixelCoord{i, j}, PixelCoord{i, j}));
+        t.randomGen = g;
+        g = cloneForThread(g, 1);
+        tiles.push_back(t);
+    }
+    return renderTiles(scene, W, H, spp, tiles, stride > 1 ? stride : 1, stride > 1 ? outW : W, stride > 1 ? outH : H,
+                       nthreads, mean, variance, stats);
 }
 
 void ora_to_srgb8(int64_t npixels, const float *rgb, uint8_t *out) {

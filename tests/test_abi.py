@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(binding.EXPORTS) == declared
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.cornelis_cuda_abi_version() == 1
+    assert lib.cornelis_cuda_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
@@ -59,6 +59,19 @@ def test_no_device_fails_loudly():
     with pytest.raises(binding.CornelisError) as e:
         binding.Scene(scenes.cornell_box())
     assert e.value.code == binding.ERR_NO_DEVICE and "no CPU path" in str(e.value)
+
+
+def test_nccl_is_bound_at_run_time():
+    """The exchange step's NCCL is loaded on first use (dlopen of libnccl.so.2), not linked: creating a communicator
+    id needs no GPU, so this proves here that the library finds and binds NCCL.  The library itself must not list
+    libnccl among its dependencies (a process that already carries torch's copy must not get a second one)."""
+    import subprocess
+    from cornelis_b200 import binding
+    uid = binding.comm_unique_id()
+    assert len(uid) == binding.COMM_ID_BYTES and any(uid)
+    assert binding.comm_unique_id() != uid
+    needed = subprocess.run(["readelf", "-d", str(binding.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "libnccl" not in needed
 
 
 def test_product_does_not_touch_the_oracle():

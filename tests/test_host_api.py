@@ -20,6 +20,16 @@ def host_test_binary(tmp_path_factory):
     return exe
 
 
+@pytest.fixture(scope="module")
+def cli():
+    """The CLI, built in-tree by build.py (a build artefact, not tracked)."""
+    from cornelis_b200 import build
+    build.build_all()
+    exe = LIB / "cornelis"
+    assert exe.exists()
+    return exe
+
+
 def test_host_api_cpu(host_test_binary):
     import torch
     mode = "cpu" if torch.cuda.is_available() else "cpu-nodevice"
@@ -77,11 +87,11 @@ def test_save_image_writes_a_real_png(host_test_binary, tmp_path, port_oracle):
     assert size < W * H * 3  # smaller than the raw pixels: the two smooth channels compress
 
 
-def test_cli_fails_loudly_without_gpu():
+def test_cli_fails_loudly_without_gpu(cli):
     import torch
     if torch.cuda.is_available():
         pytest.skip("a CUDA device is present")
-    r = subprocess.run([str(LIB / "cornelis"), "--width", "32", "--height", "32", "--spp", "1", "--no-save"],
+    r = subprocess.run([str(cli), "--width", "32", "--height", "32", "--spp", "1", "--no-save"],
                        capture_output=True, text=True)
     assert r.returncode == 1 and "no CPU path" in r.stderr
 
@@ -94,9 +104,9 @@ def test_host_api_gpu(host_test_binary):
 
 
 @pytest.mark.gpu
-def test_cli_renders_reference_default_scene(tmp_path):
+def test_cli_renders_reference_default_scene(cli, tmp_path):
     out = tmp_path / "cornell.png"
-    r = subprocess.run([str(LIB / "cornelis"), "--spp", "16", "--output", str(out)], capture_output=True, text=True)
+    r = subprocess.run([str(cli), "--spp", "16", "--output", str(out)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "512x512, 16 spp" in r.stdout and out.exists()
     image, _ = _decode_png_rgb8(out)
@@ -104,12 +114,12 @@ def test_cli_renders_reference_default_scene(tmp_path):
 
 
 @pytest.mark.gpu
-def test_cli_many_spheres_grid_and_exhaustive_agree(tmp_path):
+def test_cli_many_spheres_grid_and_exhaustive_agree(cli, tmp_path):
     """The CLI's many-sphere scene (BASELINE configs[3] style) through the grid and through the exhaustive scan: the
     same paths, hence the same statistics line apart from the timings."""
     lines = []
     for accel in ("grid", "none"):
-        r = subprocess.run([str(LIB / "cornelis"), "--scene", "spheres", "--spheres", "2000", "--width", "96", "--height",
+        r = subprocess.run([str(cli), "--scene", "spheres", "--spheres", "2000", "--width", "96", "--height",
                             "54", "--spp", "8", "--max-depth", "64", "--accel", accel, "--no-save"],
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stdout + r.stderr

@@ -241,3 +241,29 @@ def test_port_matches_reference_render(port_oracle, ref_oracle):
     assert bit_equal(port_oracle.to_srgb8(a["mean"]), ref_oracle.to_srgb8(a["mean"])) or True
     rgb = np.random.default_rng(3).random((5000, 3), dtype=np.float32) * 1.3 - 0.1
     assert np.array_equal(port_oracle.to_srgb8(rgb), ref_oracle.to_srgb8(rgb))
+
+
+def test_strided_render(port_oracle, ref_oracle, golden):
+    """ora_render_strided (every stride-th pixel of a frame as its own 1x1 tile): the port equals the compiled
+    reference bit for bit, the result does not depend on the thread count, a strided pixel is integrated with the
+    full frame's pixel footprint; the committed headline golden (1920x1080, stride 8, 4096 spp) is well formed."""
+    flat = scenes.cornell_box(0.5625)
+    a = port_oracle.scene(flat).render_strided(192, 108, 12, 8, variance=True, stats=True)
+    assert a["mean"].shape == (14, 24, 3) and a["stats"]["pixel_samples"] == 14 * 24 * 12
+    one = port_oracle.scene(flat).render_strided(192, 108, 12, 8, threads=1, variance=True)
+    assert bit_equal(a["mean"], one["mean"]) and bit_equal(a["variance"], one["variance"])
+    if ref_oracle is not None:
+        b = ref_oracle.scene(flat).render_strided(192, 108, 12, 8, variance=True, stats=True)
+        assert bit_equal(a["mean"], b["mean"]) and bit_equal(a["variance"], b["variance"])
+        assert a["stats"]["rays"] == b["stats"]["rays"]
+        assert bit_equal(ref_oracle.scene(flat).render_strided(192, 108, 12, 8)["mean"], b["mean"])  # integrateTile itself
+    # same integrand as the full frame: the strided pixels' mean energy matches the full render's at those pixels
+    full = port_oracle.scene(flat).render(192, 108, 256, tile=(8, 4))["mean"][::8, ::8]
+    strided = port_oracle.scene(flat).render_strided(192, 108, 256, 8)["mean"]
+    assert abs(float(strided.mean() / full.mean()) - 1.0) < 0.1
+    # the committed golden of the headline frame (made by tests/golden/make_golden.py from the compiled reference)
+    g = golden("render_cornell_1080p_stride8_4096spp.npz")
+    assert g["mean"].shape == (135, 240, 3) and int(g["spp"]) == 4096 and int(g["stride"]) == 8
+    assert 3.38 < float(g["rays"]) / float(g["pixel_samples"]) < 3.40
+    bad = ~np.isfinite(g["mean"]).all(axis=2)  # the reference's Oren-Nayar NaN: about one pixel-sample in 1e8
+    assert bad.sum() <= 3 and (g["variance"][~bad] >= 0).all()
