@@ -94,7 +94,7 @@ def load_fp32_peak():
         return {"peak": float(m["t_lane_ops_per_s"]), "peak_source": "measured",
                 "peak_detail": f"tools/ubench/fp32_peak.cu on {d.get('gpu', 'B200')}: alternating FMUL/FADD, "
                                f"{m['warp_inst_per_clk_per_sm']:.2f} warp instructions / clk / SM at "
-                               f"{m['effective_sm_mhz']:.0f} MHz ({FP32_PEAK_JSON.relative_to(ROOT)})",
+                               f"{d.get('sm_max_mhz', 1965.0):.0f} MHz ({FP32_PEAK_JSON.relative_to(ROOT)})",
                 "peak_computed": computed}
     return {"peak": computed, "peak_source": "computed",
             "peak_detail": "148 SM x 128 FP32 lanes x 1.965 GHz, one non-FMA operation per lane per clock "

@@ -385,10 +385,14 @@ static cudaError_t configureOne(LaunchShape &shape, int &grid) {
     shape.persistentQueueOffset = static_cast<uint32_t>(queueOffset);
     auto kernel = shape.persistentQueued ? reinterpret_cast<const void *>(k_persistent_queued<kGrid>)
                                          : reinterpret_cast<const void *>(k_persistent<kGrid>);
-    if (shape.smemOptin > 48 * 1024) // per function and device, not per scene: always the device's limit
-        if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(shape.smemOptin))) != cudaSuccess)
+    if (shape.smemOptin > 48 * 1024) { // per function and device, not per scene: always the device's limit
+        cudaFuncAttributes attr{};
+        if ((e = cudaFuncGetAttributes(&attr, kernel)) != cudaSuccess)
             return e;
+        if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(shape.smemOptin - attr.sharedSizeBytes))) != cudaSuccess)
+            return e;
+    }
     if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
         return e;

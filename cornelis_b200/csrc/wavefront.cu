@@ -758,9 +758,14 @@ cudaError_t configureKernels(LaunchShape &shape) {
                                  reinterpret_cast<const void *>(k_intersect_batch<true>),
                                  reinterpret_cast<const void *>(k_hit_surface<false>),
                                  reinterpret_cast<const void *>(k_hit_surface<true>)};
-        for (const void *kernel : staging)
-            if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, most)) != cudaSuccess)
+        for (const void *kernel : staging) { // the opt-in limit covers static + dynamic shared memory
+            cudaFuncAttributes attr{};
+            if ((e = cudaFuncGetAttributes(&attr, kernel)) != cudaSuccess)
                 return e;
+            if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          most - static_cast<int>(attr.sharedSizeBytes))) != cudaSuccess)
+                return e;
+        }
     }
     if (const char *env = std::getenv("CORNELIS_BATCH_PACKED"))
         shape.batchPacked = std::atoi(env) != 0;

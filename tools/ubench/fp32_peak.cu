@@ -5,7 +5,9 @@
 // alternating FMUL/FADD stream, FFMA, and packed FFMA2 (fma.rn.f32x2, new in sm_100).  Every mode keeps 8 independent
 // dependency chains per thread, 8 resident CTAs of 256 threads per SM.  Writes ONE JSON object to stdout:
 //     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o fp32_peak fp32_peak.cu && ./fp32_peak > fp32_peak.json
-// Rates are per second from CUDA events, and per SM clock from clock64() inside the kernel (so a throttled run shows).
+// Rates are per second from CUDA events (best of 3 after a warm-up launch); per clock they are quoted against the
+// device's maximum SM clock (cudaDevAttrClockRate).  clock64() is reported too, as ticks per second: on this part it does
+// not advance at the SM clock, so it is not used for the per-clock figures.
 #include <cstdio>
 #include <cuda_runtime.h>
 
@@ -51,6 +53,8 @@ int main() {
     if (cudaGetDeviceProperties(&prop, 0) != cudaSuccess)
         return 1;
     int const sms = prop.multiProcessorCount, perSM = 8, blocks = sms * perSM, iters = 1 << 16;
+    int clockKHz = 0;
+    cudaDeviceGetAttribute(&clockKHz, cudaDevAttrClockRate, 0);
     float *out;
     long long *cycles, *hostCycles = new long long[blocks];
     cudaMalloc(&out, blocks * 256 * sizeof(float));
@@ -58,8 +62,8 @@ int main() {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0), cudaEventCreate(&e1);
     const char *names[5] = {"fadd", "fmul", "fmul_fadd_mix", "ffma", "ffma2"};
-    std::printf("{\"gpu\": \"%s\", \"sms\": %d, \"threads_per_sm\": %d, \"chains_per_thread\": 8, \"modes\": {", prop.name, sms,
-                perSM * 256);
+    std::printf("{\"gpu\": \"%s\", \"sms\": %d, \"sm_max_mhz\": %.1f, \"threads_per_sm\": %d, \"chains_per_thread\": 8, "
+                "\"modes\": {", prop.name, sms, clockKHz / 1e3, perSM * 256);
     for (int mode = 0; mode < 5; mode++) {
         float best = 1e30f;
         for (int rep = 0; rep < 4; rep++) {
@@ -86,8 +90,8 @@ int main() {
         double const perSecond = warpInstPerSM * sms / (best * 1e-3);        // warp instructions / s, whole GPU
         int const opsPerLane = mode == 4 ? 2 : 1;
         std::printf("%s\"%s\": {\"ms\": %.4f, \"warp_inst_per_clk_per_sm\": %.4f, \"t_warp_inst_per_s\": %.4f, "
-                    "\"t_lane_ops_per_s\": %.4f, \"effective_sm_mhz\": %.1f}",
-                    mode ? ", " : "", names[mode], best, warpInstPerSM / meanCycles, perSecond / 1e12,
+                    "\"t_lane_ops_per_s\": %.4f, \"clock64_ticks_mhz\": %.1f}",
+                    mode ? ", " : "", names[mode], best, perSecond / sms / (clockKHz * 1e3), perSecond / 1e12,
                     perSecond * 32 * opsPerLane / 1e12, meanCycles / (best * 1e-3) / 1e6);
     }
     std::printf("}}\n");
