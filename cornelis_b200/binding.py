@@ -27,7 +27,8 @@ EXPORTS = [
     "cornelis_cuda_render", "cornelis_cuda_pixel_rays", "cornelis_cuda_intersect",
     "cornelis_cuda_intersect_device", "cornelis_cuda_bsdf_sample", "cornelis_cuda_bsdf_eval",
     "cornelis_cuda_shade", "cornelis_cuda_rng_uniforms", "cornelis_cuda_selftest_arith",
-    "cornelis_cuda_intersect_compact", "cornelis_cuda_selftest_srgb8",
+    "cornelis_cuda_intersect_compact", "cornelis_cuda_selftest_srgb8", "cornelis_cuda_rng_rounds",
+    "cornelis_cuda_rng_bits",
 ]
 
 OK, ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_ABORTED, ERR_NCCL = range(7)
@@ -125,6 +126,7 @@ def lib():
         L.cornelis_cuda_selftest_arith.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]
         L.cornelis_cuda_intersect_compact.argtypes = [vp, sz, f, f, f, C.POINTER(C.c_uint32), f, C.POINTER(C.c_uint32)]
         L.cornelis_cuda_selftest_srgb8.argtypes = [vp, C.c_uint32, sz, vp]
+        L.cornelis_cuda_rng_bits.argtypes = [vp, C.c_int, C.c_uint64, sz, f, f, f, f]
         _lib = L
     return _lib
 
@@ -132,6 +134,11 @@ def lib():
 def _check(rc):
     if rc != 0:
         raise CornelisError(rc, lib().cornelis_cuda_last_error().decode())
+
+
+def rng_rounds() -> int:
+    """Rounds of the render loop's Philox4x32 generator."""
+    return int(lib().cornelis_cuda_rng_rounds())
 
 
 def trim_memory() -> None:
@@ -424,6 +431,16 @@ class Scene:
         bad = C.c_uint64(0)
         _check(lib().cornelis_cuda_selftest_arith(self.handle, mode, n, seed, C.byref(bad)))
         return bad.value
+
+    def rng_bits(self, rounds, seed, pixel, sample, block):
+        """Raw Philox4x32-`rounds` words for the counters (pixel, sample, block, 0)."""
+        pixel = np.ascontiguousarray(pixel, np.uint32)
+        sample = np.ascontiguousarray(sample, np.uint32)
+        block = np.ascontiguousarray(block, np.uint32)
+        out = np.empty((len(pixel), 4), np.uint32)
+        _check(lib().cornelis_cuda_rng_bits(self.handle, rounds, seed, len(pixel), _ptr(pixel), _ptr(sample),
+                                            _ptr(block), _ptr(out)))
+        return out
 
     def rng_uniforms(self, seed, pixel, sample, block):
         pixel = np.ascontiguousarray(pixel, np.uint32)

@@ -196,6 +196,7 @@ struct cornelis_cuda_scene {
     DeviceBuffer<DevPlane> planes;
     DeviceBuffer<DevMaterial> materials;
     DeviceBuffer<uint32_t> planeOrder;
+    DeviceBuffer<DevAxisPlane> axisPlanes;
     SceneView view{};
     // acceleration structure (built on first use)
     std::vector<cornelis_sphere_desc> hostSpheres;
@@ -237,7 +238,7 @@ struct cornelis_cuda_scene {
         if (stream)
             cudaStreamSynchronize(stream);
         spheres.release(), sphereMaterial.release(), planes.release(), materials.release();
-        gridCellRange.release(), gridCellSpheres.release(), gridCellIds.release(), planeOrder.release();
+        gridCellRange.release(), gridCellSpheres.release(), gridCellIds.release(), planeOrder.release(), axisPlanes.release();
         for (auto &half : pool)
             for (auto &b : half)
                 b.release();
@@ -316,9 +317,8 @@ int checkScene(cornelis_cuda_scene *s) {
 int applyAcceleration(cornelis_cuda_scene *s, int mode) {
     size_t const nS = s->view.nSpheres, nP = s->view.nPlanes, nM = s->view.nMaterials;
     auto tableBytes = [&](bool spheresInShared) {
-        size_t const k = spheresInShared ? nS : 0;
-        size_t const order = (sizeof(uint32_t) * nP + 15u) & ~static_cast<size_t>(15u);
-        return sizeof(DevSphere) * k + sizeof(DevPlane) * nP + sizeof(DevMaterial) * nM + order + sizeof(uint32_t) * k;
+        return sharedSceneBytes(static_cast<uint32_t>(nS), static_cast<uint32_t>(nP), s->view.planeEnd[2],
+                                static_cast<uint32_t>(nM), spheresInShared);
     };
     size_t const limit = static_cast<size_t>(s->smemOptin) - 1024;
     bool wantGrid = nS > 0 && (mode == CORNELIS_ACCEL_GRID || (mode == CORNELIS_ACCEL_AUTO && nS >= kAutoGridSpheres));
@@ -483,6 +483,9 @@ int cornelis_cuda_scene_create(int device, const cornelis_camera_desc *camera, c
             classEnd[c] = static_cast<uint32_t>(k);
         }
     }
+    std::vector<DevAxisPlane> axis(classEnd[2] ? classEnd[2] : 1);
+    for (uint32_t k = 0; k < classEnd[2]; k++)
+        axis[k] = makeDevAxisPlane(hp[order[k]], static_cast<uint32_t>(n_spheres), order[k]);
     std::vector<DevMaterial> hm(n_materials);
     for (size_t i = 0; i < n_materials; i++)
         hm[i] = makeDevMaterial(materials[i].albedo, materials[i].emissive, materials[i].roughness,
@@ -493,6 +496,8 @@ int cornelis_cuda_scene_create(int device, const cornelis_camera_desc *camera, c
     CB_CUDA(s->planes.reserve(n_planes ? n_planes : 1));
     CB_CUDA(s->materials.reserve(n_materials));
     CB_CUDA(s->planeOrder.reserve(order.size()));
+    CB_CUDA(s->axisPlanes.reserve(axis.size()));
+    CB_CUDA(cudaMemcpyAsync(s->axisPlanes.ptr, axis.data(), axis.size() * sizeof(DevAxisPlane), cudaMemcpyHostToDevice, s->stream));
     CB_CUDA(cudaMemcpyAsync(s->planeOrder.ptr, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
     if (n_spheres) {
         CB_CUDA(cudaMemcpyAsync(s->spheres.ptr, hs.data(), n_spheres * sizeof(DevSphere), cudaMemcpyHostToDevice, s->stream));
@@ -512,6 +517,7 @@ int cornelis_cuda_scene_create(int device, const cornelis_camera_desc *camera, c
     s->view.nMaterials = static_cast<uint32_t>(n_materials);
     s->view.radiiSafe = radiiSafe ? 1u : 0u;
     s->view.planeOrder = s->planeOrder.ptr;
+    s->view.axisPlanes = s->axisPlanes.ptr;
     s->view.planeEnd[0] = classEnd[0], s->view.planeEnd[1] = classEnd[1], s->view.planeEnd[2] = classEnd[2];
     s->view.camera = makeCamera(*camera);
 
@@ -1086,11 +1092,11 @@ int cornelis_cuda_shade(cornelis_cuda_scene *s, size_t n, int32_t depth, const f
     return CORNELIS_OK;
 }
 
-int cornelis_cuda_rng_uniforms(cornelis_cuda_scene *s, uint64_t seed, size_t n, const uint32_t *pixel,
-                               const uint32_t *sample, const uint32_t *block, float *out) {
+static int rngCommon(cornelis_cuda_scene *s, int rounds, uint64_t seed, size_t n, const uint32_t *pixel,
+                     const uint32_t *sample, const uint32_t *block, float *uniforms, uint32_t *bits) {
     if (int rc = checkScene(s))
         return rc;
-    if (!pixel || !sample || !block || !out)
+    if (!pixel || !sample || !block || (!uniforms && !bits))
         return fail(CORNELIS_ERR_INVALID_ARGUMENT, "null argument");
     if (n == 0)
         return CORNELIS_OK;
@@ -1102,13 +1108,29 @@ int cornelis_cuda_rng_uniforms(cornelis_cuda_scene *s, uint64_t seed, size_t n, 
     CB_CUDA(cudaMemcpyAsync(b.ptr, sample, n * 4, cudaMemcpyHostToDevice, s->stream));
     CB_CUDA(cudaMemcpyAsync(c.ptr, block, n * 4, cudaMemcpyHostToDevice, s->stream));
     CB_CUDA(s->stageF[0].reserve(4 * n));
-    launchRng(s->stream, s->shape, static_cast<uint32_t>(n), static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32),
-              reinterpret_cast<const uint32_t *>(a.ptr), reinterpret_cast<const uint32_t *>(b.ptr),
-              reinterpret_cast<const uint32_t *>(c.ptr), s->stageF[0].ptr);
-    DOWNLOAD(out, s->stageF[0], 4 * n);
+    launchRng(s->stream, s->shape, static_cast<uint32_t>(n), rounds, static_cast<uint32_t>(seed),
+              static_cast<uint32_t>(seed >> 32), reinterpret_cast<const uint32_t *>(a.ptr),
+              reinterpret_cast<const uint32_t *>(b.ptr), reinterpret_cast<const uint32_t *>(c.ptr),
+              uniforms ? s->stageF[0].ptr : nullptr, bits ? reinterpret_cast<uint32_t *>(s->stageF[0].ptr) : nullptr);
+    CB_CUDA(cudaMemcpyAsync(uniforms ? static_cast<void *>(uniforms) : static_cast<void *>(bits), s->stageF[0].ptr,
+                            4 * n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
     CB_CUDA(cudaStreamSynchronize(s->stream));
     CB_CUDA(cudaGetLastError());
     return CORNELIS_OK;
+}
+
+int cornelis_cuda_rng_uniforms(cornelis_cuda_scene *s, uint64_t seed, size_t n, const uint32_t *pixel,
+                               const uint32_t *sample, const uint32_t *block, float *out) {
+    return rngCommon(s, 0, seed, n, pixel, sample, block, out, nullptr);
+}
+
+int cornelis_cuda_rng_rounds(void) { return kPhiloxRounds; }
+
+int cornelis_cuda_rng_bits(cornelis_cuda_scene *s, int rounds, uint64_t seed, size_t n, const uint32_t *pixel,
+                           const uint32_t *sample, const uint32_t *block, uint32_t *out) {
+    if (rounds < 1 || rounds > 16)
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "rounds must be in [1, 16]");
+    return rngCommon(s, rounds, seed, n, pixel, sample, block, nullptr, out);
 }
 
 int cornelis_cuda_selftest_srgb8(cornelis_cuda_scene *s, uint32_t firstBits, size_t n, uint8_t *hostOut) {

@@ -27,6 +27,17 @@ struct __align__(16) DevPlane {    // 4 x float4
     float bx, by, bz; uint32_t pad;      // constructBasis(normal).B; pad = axis class: 0/1/2 normal = +-x/y/z, 3 general
 };
 
+// Axis-aligned planes once more, as closestHit's fast path reads them (geometry.cuh axisPlaneTest): per plane two float4,
+// class by class (normal along x, then y, then z; by index within a class):
+//     (p0_k, p0_T, p0_B, width / 2)   (height / 2, primitive id as int bits, 0, 0)
+// with k the normal's axis and T, B the in-plane axes constructBasis gives that class.
+struct __align__(16) DevAxisPlane {
+    float p0k, p0T, p0B, halfWidth;
+    float halfHeight;
+    int32_t id;
+    uint32_t pad0, pad1;
+};
+
 struct __align__(16) DevMaterial { // 4 x float4 — StandardMaterial (Materials.hpp:325-338) with its constants folded
     float er, eg, eb, on_a;        // emission; OrenNayarBRDF::a_ (Materials.hpp:208)
     float dr, dg, db, on_b;        // albedo / Pi (Materials.hpp:226, Color.cpp:11-17); OrenNayarBRDF::b_
@@ -71,21 +82,33 @@ struct SceneView {
     // planeEnd[1]) along y, [planeEnd[1], planeEnd[2]) along z, the rest are general.  closestHit runs one tight loop
     // per class instead of dispatching on the class of every plane.
     const uint32_t *planeOrder;
+    const DevAxisPlane *axisPlanes; // planeEnd[2] records
     uint32_t planeEnd[3];
     uint32_t pad2;
     DevCamera camera;
     DevGrid grid;
 };
 
-// Scene tables staged in dynamic shared memory: [spheres][planes][materials][plane order][sphere material ids]
-// (kernels.cuh stageScene).  With the grid the sphere tables stay in global memory and the pointers say so.
+// Scene tables staged in dynamic shared memory: [spheres][planes][materials][axis planes][plane order][sphere
+// material ids] (kernels.cuh stageScene).  With the grid the sphere tables stay in global memory and the pointers say so.
 struct SharedScene {
     const DevSphere *spheres;
     const DevPlane *planes;
     const DevMaterial *materials;
+    const float4 *axisPlanes; // DevAxisPlane records as float4 pairs
     const uint32_t *planeOrder;
     const uint32_t *sphereMaterial;
 };
+
+// With the grid enabled the spheres (and their material ids) stay in global memory — a ray touches a few dozen of
+// them through the read-only cache — and only planes, materials and the plane order are staged.
+__host__ __device__ inline size_t sharedSceneBytes(uint32_t nSpheres, uint32_t nPlanes, uint32_t nAxisPlanes,
+                                                   uint32_t nMaterials, bool spheresInShared) {
+    size_t const s = spheresInShared ? nSpheres : 0u;
+    size_t const order = (sizeof(uint32_t) * nPlanes + 15u) & ~static_cast<size_t>(15u);
+    return sizeof(DevSphere) * s + sizeof(DevPlane) * nPlanes + sizeof(DevMaterial) * nMaterials +
+           sizeof(DevAxisPlane) * nAxisPlanes + order + sizeof(uint32_t) * s;
+}
 
 // Path pool: four float4 arrays — 64 B per path.
 //   org  = ray origin xyz | unused

@@ -28,16 +28,6 @@ constexpr int kWarpsPerBlock = kBlockThreads / 32;
 
 // --------------------------------------------------------------------------------------------- shared scene --
 
-// With the grid enabled the spheres (and their material ids) stay in global memory — a ray touches a few dozen of
-// them through the read-only cache — and only planes, materials and the plane order are staged.
-__host__ __device__ inline size_t sharedSceneBytes(uint32_t nSpheres, uint32_t nPlanes, uint32_t nMaterials,
-                                                   bool spheresInShared) {
-    size_t const s = spheresInShared ? nSpheres : 0u;
-    size_t const order = (sizeof(uint32_t) * nPlanes + 15u) & ~static_cast<size_t>(15u);
-    return sizeof(DevSphere) * s + sizeof(DevPlane) * nPlanes + sizeof(DevMaterial) * nMaterials + order +
-           sizeof(uint32_t) * s;
-}
-
 // Cooperative 16-byte copies global -> shared; every table is a multiple of 16 bytes except the two index lists.
 // kGrid is a compile-time parameter so that, without the grid, every pointer provably addresses shared memory
 // (LDS.128 instead of generic loads).
@@ -47,10 +37,12 @@ __device__ __forceinline__ SharedScene stageScene(const SceneView &scene, unsign
     uint32_t const nS4 = kGrid ? 0u : scene.nSpheres;             // 1 float4 per sphere
     uint32_t const nP4 = scene.nPlanes * 4;                       // 4 float4 per plane
     uint32_t const nM4 = scene.nMaterials * 4;                    // 4 float4 per material
+    uint32_t const nA4 = scene.planeEnd[2] * 2;                   // 2 float4 per axis-aligned plane
     uint32_t const nO4 = (scene.nPlanes + 3u) / 4u;               // plane order, padded to 16 bytes
     const float4 *srcS = reinterpret_cast<const float4 *>(scene.spheres);
     const float4 *srcP = reinterpret_cast<const float4 *>(scene.planes);
     const float4 *srcM = reinterpret_cast<const float4 *>(scene.materials);
+    const float4 *srcA = reinterpret_cast<const float4 *>(scene.axisPlanes);
     for (uint32_t k = threadIdx.x; k < nS4; k += blockDim.x)
         dst[k] = srcS[k];
     for (uint32_t k = threadIdx.x; k < nP4; k += blockDim.x)
@@ -58,10 +50,12 @@ __device__ __forceinline__ SharedScene stageScene(const SceneView &scene, unsign
     if (wantMaterials)
         for (uint32_t k = threadIdx.x; k < nM4; k += blockDim.x)
             dst[nS4 + nP4 + k] = srcM[k];
-    uint32_t *order = reinterpret_cast<uint32_t *>(dst + nS4 + nP4 + nM4);
+    for (uint32_t k = threadIdx.x; k < nA4; k += blockDim.x)
+        dst[nS4 + nP4 + nM4 + k] = srcA[k];
+    uint32_t *order = reinterpret_cast<uint32_t *>(dst + nS4 + nP4 + nM4 + nA4);
     for (uint32_t k = threadIdx.x; k < scene.nPlanes; k += blockDim.x)
         order[k] = scene.planeOrder[k];
-    uint32_t *ids = reinterpret_cast<uint32_t *>(dst + nS4 + nP4 + nM4 + nO4);
+    uint32_t *ids = reinterpret_cast<uint32_t *>(dst + nS4 + nP4 + nM4 + nA4 + nO4);
     if (wantMaterials && !kGrid)
         for (uint32_t k = threadIdx.x; k < scene.nSpheres; k += blockDim.x)
             ids[k] = scene.sphereMaterial[k];
@@ -70,6 +64,7 @@ __device__ __forceinline__ SharedScene stageScene(const SceneView &scene, unsign
     s.spheres = kGrid ? scene.spheres : reinterpret_cast<const DevSphere *>(dst);
     s.planes = reinterpret_cast<const DevPlane *>(dst + nS4);
     s.materials = reinterpret_cast<const DevMaterial *>(dst + nS4 + nP4);
+    s.axisPlanes = dst + nS4 + nP4 + nM4;
     s.planeOrder = order;
     s.sphereMaterial = kGrid ? scene.sphereMaterial : ids;
     return s;

@@ -29,23 +29,32 @@ namespace cornelis_b200 {
 
 constexpr unsigned long long kMaxClaim = 1024; // camera paths a warp claims per atomic (RenderConfig::claim <= this)
 
-// CTA shape of the persistent kernels, measured on B200 with the queued variant (Cornell 1080p, Msamples/s):
+// CTA shape of the persistent kernels, measured on B200 with the queued variant (Cornell 1080p, Msamples/s).
+// Round 1 (hot loop ~28 KB against a 32 KB instruction cache, 72 registers wanted):
 //   256 threads x 4 CTAs/SM (64 registers, 32 warps/SM) 6332     256 x 3 (80 registers, 24 warps) 7103
-//   256 x 2 (128 registers, 16 warps) 7260    128 x 7 (72, 28 warps) 7036    128 x 6 (80, 24 warps) 7396
-//   128 x 5 (96 registers, 20 warps/SM) 7509
-// The loop body is ~28 KB of hot code against a 32 KB instruction cache, and at 64 registers ptxas rematerialises
-// and spills: fewer, fatter warps issue fewer instructions and fetch from fewer places at once.
+//   256 x 2 (128 registers, 16 warps) 7260    128 x 6 (80, 24 warps) 7396    128 x 7 (72 registers, 28 warps) 7509
+// Round 2 (branch-free plane tests, 7 Philox rounds: a smaller loop that fits 64 registers without spills or
+// rematerialisation — the same 2952 instructions at either budget; profiles/r2_persistent/variants.log):
+//   128 x 6 (78 registers, 24 warps) 7947     128 x 7 (64 registers) 8097     128 x 8 (64 registers, 32 warps/SM) 8240
+// A minimum of 7 CTAs per SM makes ptxas settle on 64 registers, and the occupancy calculator then finds room for 8.
 #ifndef CORNELIS_PERSISTENT_MIN_BLOCKS
-#define CORNELIS_PERSISTENT_MIN_BLOCKS 5
+#define CORNELIS_PERSISTENT_MIN_BLOCKS 7
 #endif
 #ifndef CORNELIS_PERSISTENT_THREADS
 #define CORNELIS_PERSISTENT_THREADS 128
 #endif
 constexpr int kPersistentThreads = CORNELIS_PERSISTENT_THREADS; // CTA size of the persistent kernels
 constexpr int kPersistentWarps = kPersistentThreads / 32;
+// Register budget: either a minimum number of resident CTAs (ptxas derives the cap) or an explicit cap
+// (-DCORNELIS_PERSISTENT_MAXNREG=n; the two qualifiers exclude each other).
+#ifdef CORNELIS_PERSISTENT_MAXNREG
+#define CB_PERSISTENT_BOUNDS __maxnreg__(CORNELIS_PERSISTENT_MAXNREG)
+#else
+#define CB_PERSISTENT_BOUNDS __launch_bounds__(kPersistentThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
+#endif
 
 template <bool kGrid>
-__global__ void __launch_bounds__(kPersistentThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
+__global__ void CB_PERSISTENT_BOUNDS
     k_persistent(RenderConfig cfg, SceneView scene, unsigned long long *__restrict__ cursor, unsigned long long limit,
                  float4 *__restrict__ accum, float4 *__restrict__ accum2, bool dropNonFinite, Control *__restrict__ ctl) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -117,7 +126,7 @@ __global__ void __launch_bounds__(kPersistentThreads, CORNELIS_PERSISTENT_MIN_BL
                     pixel = newPixel;
                     sample = cfg.firstSample + newSample;
                     uint32_t const j = fastDivide(pixel, cfg.byWidth), i = pixel - j * cfg.width;
-                    Philox4 const r = philox4x32_10(pixel, sample, 0u, 0u, cfg.keys);
+                    Philox4 const r = philoxRender(pixel, sample, 0u, 0u, cfg.keys);
                     dir = pixelRayDirection(scene.camera, i, j, cfg.dx, cfg.dy, uniformFromBits(r.v[0]),
                                             uniformFromBits(r.v[1]));
                     org = V3{scene.camera.ex, scene.camera.ey, scene.camera.ez};
@@ -147,7 +156,7 @@ __global__ void __launch_bounds__(kPersistentThreads, CORNELIS_PERSISTENT_MIN_BL
                 V3 P, N;
                 uint32_t material;
                 hitSurface(org, dir, t, prim, sh.spheres, sh.sphereMaterial, scene.nSpheres, sh.planes, P, N, material);
-                Philox4 const r = philox4x32_10(pixel, sample, depth + 1u, 0u, cfg.keys);
+                Philox4 const r = philoxRender(pixel, sample, depth + 1u, 0u, cfg.keys);
                 bool const survives =
                     shadeBounce(sh.materials[material], P, N, depth, uniformFromBits(r.v[0]), uniformFromBits(r.v[1]),
                                 uniformFromBits(r.v[2]), uniformFromBits(r.v[3]), org, dir, thr, rad);
@@ -205,7 +214,7 @@ constexpr uint32_t kQueueChunks = 5;
 constexpr size_t kQueueBytesPerWarp = kQueueSlots * kQueueChunks * sizeof(float4);
 
 template <bool kGrid>
-__global__ void __launch_bounds__(kPersistentThreads, CORNELIS_PERSISTENT_MIN_BLOCKS)
+__global__ void CB_PERSISTENT_BOUNDS
     k_persistent_queued(RenderConfig cfg, SceneView scene, unsigned long long *__restrict__ cursor,
                         unsigned long long limit, float4 *__restrict__ accum, float4 *__restrict__ accum2,
                         bool dropNonFinite, Control *__restrict__ ctl, uint32_t queueOffset) {
@@ -285,7 +294,7 @@ __global__ void __launch_bounds__(kPersistentThreads, CORNELIS_PERSISTENT_MIN_BL
                 pixel = newPixel;
                 sample = cfg.firstSample + newSample;
                 uint32_t const j = fastDivide(pixel, cfg.byWidth), i = pixel - j * cfg.width;
-                Philox4 const r = philox4x32_10(pixel, sample, 0u, 0u, cfg.keys);
+                Philox4 const r = philoxRender(pixel, sample, 0u, 0u, cfg.keys);
                 dir = pixelRayDirection(scene.camera, i, j, cfg.dx, cfg.dy, uniformFromBits(r.v[0]),
                                         uniformFromBits(r.v[1]));
                 org = V3{scene.camera.ex, scene.camera.ey, scene.camera.ez};
@@ -316,7 +325,7 @@ __global__ void __launch_bounds__(kPersistentThreads, CORNELIS_PERSISTENT_MIN_BL
                 uint32_t const material = static_cast<uint32_t>(prim) < scene.nSpheres
                                               ? sh.sphereMaterial[prim]
                                               : sh.planes[prim - static_cast<int32_t>(scene.nSpheres)].material;
-                Philox4 const r = philox4x32_10(pixel, sample, depth + 1u, 0u, cfg.keys);
+                Philox4 const r = philoxRender(pixel, sample, depth + 1u, 0u, cfg.keys);
                 bool const survives =
                     shadeRoulette(sh.materials[material], depth, uniformFromBits(r.v[0]), thr, rad, prob);
                 x0 = uniformFromBits(r.v[1]), x1 = uniformFromBits(r.v[2]), x2 = uniformFromBits(r.v[3]);

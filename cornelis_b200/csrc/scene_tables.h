@@ -38,8 +38,29 @@ inline DevPlane makeDevPlane(const cornelis_plane_desc &d) {
     auto safe = [](float x) { return !(fabsf(x) < 0x1.0p-56f) || x == 0.0f; };
     bool const finite = std::isfinite(p.px) && std::isfinite(p.py) && std::isfinite(p.pz) &&
                         fabsf(p.px) <= 0x1.0p30f && fabsf(p.py) <= 0x1.0p30f && fabsf(p.pz) <= 0x1.0p30f;
-    p.pad = expected && finite && safe(p.px) && safe(p.py) && safe(p.pz) ? static_cast<uint32_t>(kN) : 3u;
+    // ... and compares |e| against HALF the extents (axisPlaneTest): the halving must be exact, i.e. an extent is 0, NaN,
+    // infinite or at least 2^-100 in magnitude
+    auto halves = [](float w) { return w == 0.0f || !(fabsf(w) < 0x1.0p-100f); };
+    p.pad = expected && finite && safe(p.px) && safe(p.py) && safe(p.pz) && halves(p.width) && halves(p.height)
+                ? static_cast<uint32_t>(kN)
+                : 3u;
     return p;
+}
+
+// The compact record of an axis-aligned plane (device_types.h DevAxisPlane); `index` is the plane's position in the
+// scene's plane list, its primitive id is nSpheres + index.
+inline DevAxisPlane makeDevAxisPlane(const DevPlane &p, uint32_t nSpheres, uint32_t index) {
+    float const point[3] = {p.px, p.py, p.pz};
+    int const k = static_cast<int>(p.pad);          // 0, 1, 2
+    int const axisT = k == 0 ? 2 : 0, axisB = k == 1 ? 2 : 1; // constructBasis: x -> (T z, B y); y -> (T x, B z); z -> (T x, B y)
+    DevAxisPlane a{};
+    a.p0k = point[k];
+    a.p0T = point[axisT];
+    a.p0B = point[axisB];
+    a.halfWidth = p.width * 0.5f;
+    a.halfHeight = p.height * 0.5f;
+    a.id = static_cast<int32_t>(nSpheres + index);
+    return a;
 }
 
 // Bounding box of everything a ray of the render loop can start from: the camera eye, the sphere boxes and the

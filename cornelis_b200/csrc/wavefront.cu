@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_raygen(const Control *ctl, Re
         pixel -= wraps * cfg.npixels;
         uint32_t const sample = cfg.firstSample + sample0 + wraps;
         uint32_t const j = fastDivide(pixel, cfg.byWidth), i = pixel - j * cfg.width;
-        Philox4 const r = philox4x32_10(pixel, sample, 0u, 0u, cfg.keys);
+        Philox4 const r = philoxRender(pixel, sample, 0u, 0u, cfg.keys);
         float const phi1 = uniformFromBits(r.v[0]), phi2 = uniformFromBits(r.v[1]); // Render.cpp:94-95
         V3 const d = pixelRayDirection(cam, i, j, cfg.dx, cfg.dy, phi1, phi2);
         uint32_t const slot = base + k;
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_SHADE_MIN_BLOCKS) k_sh
             V3 P, N;
             uint32_t material;
             hitSurface(org, dir, h.t, h.prim, sh.spheres, sh.sphereMaterial, scene.nSpheres, sh.planes, P, N, material);
-            Philox4 const r = philox4x32_10(pixel, sample, depth + 1u, 0u, cfg.keys);
+            Philox4 const r = philoxRender(pixel, sample, depth + 1u, 0u, cfg.keys);
             alive = shadeBounce(sh.materials[material], P, N, depth, uniformFromBits(r.v[0]), uniformFromBits(r.v[1]),
                                 uniformFromBits(r.v[2]), uniformFromBits(r.v[3]), org, dir, thr, rad);
             depth += 1;
@@ -520,12 +520,20 @@ __global__ void __launch_bounds__(kBlockThreads) k_shade_explicit(const DevMater
     }
 }
 
-__global__ void __launch_bounds__(kBlockThreads) k_rng(uint32_t n, uint32_t key0, uint32_t key1, const uint32_t *pixel,
-                                                       const uint32_t *sample, const uint32_t *block, float *out) {
+// rounds == 0: the render loop's generator (philoxRender over the expanded keys), as the kernels call it; otherwise
+// Philox4x32 with that many rounds.  Writes the four uniforms and / or the four raw words of every counter.
+__global__ void __launch_bounds__(kBlockThreads) k_rng(uint32_t n, int rounds, uint32_t key0, uint32_t key1,
+                                                       PhiloxKeys keys, const uint32_t *pixel, const uint32_t *sample,
+                                                       const uint32_t *block, float *uniforms, uint32_t *bits) {
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        Philox4 const r = philox4x32_10(pixel[k], sample[k], block[k], 0u, key0, key1);
-        for (int c = 0; c < 4; c++)
-            out[4 * k + c] = uniformFromBits(r.v[c]);
+        Philox4 const r = rounds == 0 ? philoxRender(pixel[k], sample[k], block[k], 0u, keys)
+                                      : philox4x32(rounds, pixel[k], sample[k], block[k], 0u, key0, key1);
+        for (int c = 0; c < 4; c++) {
+            if (uniforms)
+                uniforms[4 * k + c] = uniformFromBits(r.v[c]);
+            if (bits)
+                bits[4 * k + c] = r.v[c];
+        }
     }
 }
 
@@ -538,7 +546,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_selftest_arith(int mode, unsi
     unsigned long long bad = 0;
     for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
-        Philox4 const r = philox4x32_10(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), 0x5e1f7e57u, 0u, seed, 0u);
+        Philox4 const r = philox4x32(10, static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), 0x5e1f7e57u, 0u, seed, 0u);
         auto craft = [](uint32_t bits, uint32_t style, int eLo, int eHi) {
             uint32_t mant = bits & 0x7fffffu;
             switch (style & 7u) {
@@ -723,9 +731,10 @@ void launchShadeExplicit(cudaStream_t s, const LaunchShape &shape, const DevMate
                                                                            thr, rad, alive);
 }
 
-void launchRng(cudaStream_t s, const LaunchShape &shape, uint32_t n, uint32_t key0, uint32_t key1,
-               const uint32_t *pixel, const uint32_t *sample, const uint32_t *block, float *out) {
-    k_rng<<<gridFor(n, shape.numSMs, 8), kBlockThreads, 0, s>>>(n, key0, key1, pixel, sample, block, out);
+void launchRng(cudaStream_t s, const LaunchShape &shape, uint32_t n, int rounds, uint32_t key0, uint32_t key1,
+               const uint32_t *pixel, const uint32_t *sample, const uint32_t *block, float *uniforms, uint32_t *bits) {
+    k_rng<<<gridFor(n, shape.numSMs, 8), kBlockThreads, 0, s>>>(n, rounds, key0, key1, makePhiloxKeys(key0, key1), pixel,
+                                                                sample, block, uniforms, bits);
 }
 
 void launchSelftestArith(cudaStream_t s, const LaunchShape &shape, int mode, unsigned long long n, uint32_t seed,

@@ -68,8 +68,8 @@ void launchBsdfEval(cudaStream_t s, const LaunchShape &shape, const DevMaterial 
 void launchShadeExplicit(cudaStream_t s, const LaunchShape &shape, const DevMaterial *materials, uint32_t n,
                          uint32_t depth, const float *u, const float *P, const float *N, const int32_t *mat,
                          float *org, float *dir, float *thr, float *rad, uint8_t *alive);
-void launchRng(cudaStream_t s, const LaunchShape &shape, uint32_t n, uint32_t key0, uint32_t key1,
-               const uint32_t *pixel, const uint32_t *sample, const uint32_t *block, float *out);
+void launchRng(cudaStream_t s, const LaunchShape &shape, uint32_t n, int rounds, uint32_t key0, uint32_t key1,
+               const uint32_t *pixel, const uint32_t *sample, const uint32_t *block, float *uniforms, uint32_t *bits);
 void launchSelftestArith(cudaStream_t s, const LaunchShape &shape, int mode, unsigned long long n, uint32_t seed,
                           unsigned long long *mismatches);
 void launchPack4(cudaStream_t s, const LaunchShape &shape, size_t n, const float *xyz, float4 *out);

@@ -256,12 +256,18 @@ int cornelis_cuda_shade(cornelis_cuda_scene *scene, size_t n, int32_t depth, con
                         const float *N, const int32_t *mat, float *org, float *dir, float *thr, float *rad,
                         uint8_t *alive);
 
-/* The counter-based generator that replaces the per-tile xoshiro stream (PRNG.hpp:11-37): Philox4x32-10 keyed by
- * `seed`, counter (pixel, sample, dimension block).  out[4*n] = the four U[0,1) floats of each counter, with the
- * reference's 24-bit mapping (u >> 8) * 2^-24 (XoshiroCpp.hpp:651-655).  Block 0 feeds the camera jitter, block
- * d+1 the bounce at depth d. */
+/* The counter-based generator that replaces the per-tile xoshiro stream (PRNG.hpp:11-37): Philox4x32 with
+ * cornelis_cuda_rng_rounds() rounds (7: Crush-resistant per Salmon et al., SC'11; see cornelis_b200/csrc/rng.cuh), keyed
+ * by `seed`, counter (pixel, sample, dimension block, 0).  out[4*n] = the four U[0,1) floats of each counter, with the
+ * reference's 24-bit mapping (u >> 8) * 2^-24 (XoshiroCpp.hpp:651-655), produced by the render kernels' own code path.
+ * Block 0 feeds the camera jitter, block d+1 the bounce at depth d. */
 int cornelis_cuda_rng_uniforms(cornelis_cuda_scene *scene, uint64_t seed, size_t n, const uint32_t *pixel,
                                const uint32_t *sample, const uint32_t *block, float *out);
+int cornelis_cuda_rng_rounds(void);
+/* The raw 4x32-bit words of Philox4x32 with an explicit number of rounds (1..16), same key and counter layout: lets a
+ * test put the published 10-round known-answer vectors through the library's round function. */
+int cornelis_cuda_rng_bits(cornelis_cuda_scene *scene, int rounds, uint64_t seed, size_t n, const uint32_t *pixel,
+                           const uint32_t *sample, const uint32_t *block, uint32_t *out);
 
 /* Device self-test of the hand-scheduled exact arithmetic (cornelis_b200/csrc/exact_arith.cuh) against the IEEE
  * operators: mode 0 division, mode 1 square root (n crafted operand pairs, zeros and out-of-range operands included),

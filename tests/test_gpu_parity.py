@@ -408,35 +408,58 @@ def test_shade_step(binding, oracle, golden):
 
 # ---------------------------------------------------------------------------------------------------------- rng --
 
-def _philox_numpy(c0, c1, c2, k0, k1):
-    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85)
+def _philox_numpy(c0, c1, c2, k0, k1, rounds=10, c3=0):
+    """Philox4x32-`rounds` (Salmon et al., SC'11) on uint32 arrays: counter (c0, c1, c2, c3), key (k0, k1)."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
     mask, sh = np.uint64(0xFFFFFFFF), np.uint64(32)
-    c = [c0.astype(np.uint64), c1.astype(np.uint64), c2.astype(np.uint64), np.zeros_like(c0, np.uint64)]
+    c = [np.asarray(x, np.uint64) for x in (c0, c1, c2, np.full(np.shape(c0), c3, np.uint64))]
     k0, k1 = np.uint64(k0), np.uint64(k1)
-    for _ in range(10):
-        p0, p1 = M0 * c[0], M1 * c[2]
+    for _ in range(rounds):
+        p0, p1 = np.uint64(M0) * c[0], np.uint64(M1) * c[2]
         c = [(p1 >> sh) ^ c[1] ^ k0, p1 & mask, (p0 >> sh) ^ c[3] ^ k1, p0 & mask]
-        k0, k1 = (k0 + W0) & mask, (k1 + W1) & mask
+        k0, k1 = (k0 + np.uint64(W0)) & mask, (k1 + np.uint64(W1)) & mask
     return np.stack(c, axis=1).astype(np.uint32)
 
 
 def test_counter_rng(binding):
+    """The render loop's generator is Philox4x32 with rng_rounds() = 7 rounds.  (1) The numpy restatement reproduces the
+    Random123 known-answer vectors of philox4x32-10; (2) so does the library's round function on the device
+    (cornelis_cuda_rng_bits at 10 rounds); (3) the device's 7-round words, and the uniforms the render kernels' own code
+    path produces, equal the restatement's at 7 rounds, with the reference's 24-bit float mapping."""
     sc = binding.Scene(scenes.cornell_box())
+    rounds = binding.rng_rounds()
+    assert rounds == 7
+    # Random123 kat_vectors, philox4x32 10: (counter, key) -> output
+    z, ones = np.zeros(1, np.uint32), np.full(1, 0xFFFFFFFF, np.uint32)
+    assert [hex(v) for v in _philox_numpy(z, z, z, 0, 0)[0]] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    assert [hex(v) for v in _philox_numpy(ones, ones, ones, 0xFFFFFFFF, 0xFFFFFFFF, c3=0xFFFFFFFF)[0]] == \
+        ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+    pi = [np.array([v], np.uint32) for v in (0x243f6a88, 0x85a308d3, 0x13198a2e)]  # digits of pi: counter and key
+    assert [hex(v) for v in _philox_numpy(*pi, 0xa4093822, 0x299f31d0, c3=0x03707344)[0]] == \
+        ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+    assert [hex(v) for v in sc.rng_bits(10, 0, z, z, z)[0]] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
     rng = np.random.default_rng(3)
     n = 1 << 16
     pixel = rng.integers(0, 1 << 23, n).astype(np.uint32)
     sample = rng.integers(0, 1 << 14, n).astype(np.uint32)
     block = rng.integers(0, 16, n).astype(np.uint32)
     seed = 19791102 | (7 << 32)
+    for r in (7, 10):
+        assert np.array_equal(sc.rng_bits(r, seed, pixel, sample, block),
+                              _philox_numpy(pixel, sample, block, seed & 0xFFFFFFFF, seed >> 32, rounds=r))
     u = sc.rng_uniforms(seed, pixel, sample, block)
-    bits = _philox_numpy(pixel, sample, block, seed & 0xFFFFFFFF, seed >> 32)
+    bits = _philox_numpy(pixel, sample, block, seed & 0xFFFFFFFF, seed >> 32, rounds=rounds)
     expect = (bits >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)  # XoshiroCpp.hpp:651-655 mapping
     assert bit_equal(u, expect)
     assert (u >= 0).all() and (u < 1).all()
     assert abs(u.mean() - 0.5) < 0.005 and abs(u.var() - 1 / 12) < 0.002
-    # Random123 known-answer vector for philox4x32-10: counter 0, key 0
-    z = np.zeros(1, np.uint32)
-    assert [hex(v) for v in _philox_numpy(z, z, z, 0, 0)[0]] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    # neighbouring counters (consecutive pixels, samples and bounces are what a render draws) are uncorrelated
+    grid = sc.rng_uniforms(seed, np.arange(n, dtype=np.uint32), np.zeros(n, np.uint32), np.ones(n, np.uint32))
+    for lag in (1, 2, 1920):
+        for a in range(4):
+            for b in range(4):
+                assert abs(np.corrcoef(grid[:-lag, a], grid[lag:, b])[0, 1]) < 0.02
+    assert abs(np.corrcoef(grid[:, 0], grid[:, 1])[0, 1]) < 0.02
 
 
 # ------------------------------------------------------------------------------------------------------- images --
@@ -507,7 +530,7 @@ def test_headline_frame_within_three_sigma(binding, golden):
     print(f"headline frame, {good.sum()} strided pixels: 3-sigma fraction {frac:.5f}  RMSE {rmse:.5f}  relRMSE "
           f"{rel_rmse:.5f}  energy ratio {energy:.5f}  z mean {zz.mean():.4f} std {zz.std():.4f}  non-finite pixels in "
           f"the whole frame {int((~np.isfinite(mean).all(axis=2)).sum())}")
-    assert (~good).sum() <= 2
+    assert (~good).sum() <= 8  # the reference's NaN quirk, on either side: about one pixel-sample in 1e8
     assert frac >= 0.99, frac
     assert abs(energy - 1.0) < 0.01 and rel_rmse < 0.12
     assert abs(zz.mean()) < 0.05 and 0.8 < zz.std() < 1.2
