@@ -195,13 +195,14 @@ __device__ __forceinline__ bool shadeRoulette(const DevMaterial &mat, uint32_t d
 
 // Second half, Render.cpp:194-213: sample the layered BSDF at the hit, build the next ray and update the throughput.
 // dir is the incoming ray's direction on entry and the sampled direction on exit.
+// `odd`: see normalize (math.cuh) — the caller redoes the step without it when it comes back raised.
 __device__ __forceinline__ void shadeScatter(const DevMaterial &mat, V3 P, V3 N, float prob, float x0, float x1, float x2,
-                                             V3 &org, V3 &dir, RGBf &thr) {
+                                             V3 &org, V3 &dir, RGBf &thr, bool *odd = nullptr) {
     V3 const wOut = -dir;                                                   // Render.cpp:174
-    Basis const basis = constructBasis(N);                                  // Render.cpp:194
+    Basis const basis = constructBasis(N, odd);                             // Render.cpp:194
     V3 wIn;
     float pdf;
-    RGBf const f = layeredSample(mat, wOut, x0, x1, x2, basis, wIn, pdf);   // Render.cpp:200
+    RGBf const f = layeredSample(mat, wOut, x0, x1, x2, basis, wIn, pdf, odd); // Render.cpp:200
     org = P + wIn * 0.0001f;                                                // Render.cpp:207
     dir = wIn;                                                              // Render.cpp:208
     float const c = fabsf(dot(wIn, N));

@@ -132,8 +132,8 @@ __device__ __forceinline__ RGBf orenNayarEval(const DevMaterial &m, V3 wi, V3 wo
 
 // GlossyBRDF::operator() (Materials.hpp:130-154) and GlossyBRDF::pdf (Materials.hpp:177-188) share the half vector
 // h = normalize(wi + wo), its cosine and D; evaluated together.  Returns the scalar that multiplies the tint.
-__device__ __forceinline__ float glossyEvalPdf(const DevMaterial &m, V3 wi, V3 wo, V3 N, float &pdf) {
-    V3 const h = normalize(wi + wo);                       // exact chain
+__device__ __forceinline__ float glossyEvalPdf(const DevMaterial &m, V3 wi, V3 wo, V3 N, float &pdf, bool *odd = nullptr) {
+    V3 const h = normalize(wi + wo, odd);                  // exact chain
     float const cosThetaH = stdMax(0.0f, dot(h, N));
     float D = 1.0f;
     if (isAlmostZero(cosThetaH)) {
@@ -161,9 +161,9 @@ __device__ __forceinline__ float glossyEvalPdf(const DevMaterial &m, V3 wi, V3 w
 
 // LayeredBRDF::operator() and ::pdf (Materials.hpp:255-277): f = (1 - F(N.wi)) * diffuse + glossy;
 // pdf = 0.5 * (1/(2 Pi) + pdf_glossy) — the unweighted average whatever lobe was sampled.
-__device__ __forceinline__ RGBf layeredEvalPdf(const DevMaterial &m, V3 wi, V3 wo, V3 N, float &pdf) {
+__device__ __forceinline__ RGBf layeredEvalPdf(const DevMaterial &m, V3 wi, V3 wo, V3 N, float &pdf, bool *odd = nullptr) {
     float pdfGlossy;
-    float const g = glossyEvalPdf(m, wi, wo, N, pdfGlossy);
+    float const g = glossyEvalPdf(m, wi, wo, N, pdfGlossy, odd);
     pdf = fma1(0.5f, pdfGlossy, 0.5f * kHemispherePdf);
     RGBf const Df = orenNayarEval(m, wi, wo);
     RGBf const Gf = RGBf{m.tr, m.tg, m.tb} * g;
@@ -181,8 +181,9 @@ __device__ __forceinline__ RGBf layeredEvalPdf(const DevMaterial &m, V3 wi, V3 w
 //     glossy:  angle = 2 Pi x0, radial = sin(theta_h),           axial = cos(theta_h) = sqrt((1-x1)/(1+(a^2-1)x1))
 // The lobe's own f/pdf are discarded by the reference (Materials.hpp:281-289); pdf and f come from the layered
 // functions at the sampled wi.  If the half vector falls below the surface wi stays 0 (Materials.hpp:169-170).
+// `odd`: see normalize (math.cuh).
 __device__ __forceinline__ RGBf layeredSample(const DevMaterial &m, V3 wo, float x0, float x1, float x2,
-                                              const Basis &b, V3 &wi, float &pdf) {
+                                              const Basis &b, V3 &wi, float &pdf, bool *odd = nullptr) {
     bool const diffuse = x2 < 0.5f;
     float radial, axial;
     if (diffuse) {
@@ -204,11 +205,11 @@ __device__ __forceinline__ RGBf layeredSample(const DevMaterial &m, V3 wo, float
     wi = v;
     if (!diffuse) {
         wi = V3{0.0f, 0.0f, 0.0f};
-        V3 const h = normalize(v);
+        V3 const h = normalize(v, odd);
         if (!(dot(h, b.N) < 0.0f))
-            wi = normalize((2.0f * dot(wo, h)) * h - wo);
+            wi = normalize((2.0f * dot(wo, h)) * h - wo, odd);
     }
-    return layeredEvalPdf(m, wi, wo, b.N, pdf);
+    return layeredEvalPdf(m, wi, wo, b.N, pdf, odd);
 }
 
 // russianRouletteFactor, Render.cpp:153-165.

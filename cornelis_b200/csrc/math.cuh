@@ -6,6 +6,7 @@
 #pragma once
 
 #include <cmath>
+#include <cstdint>
 #include <cuda_runtime.h>
 
 #ifndef CB_HD
@@ -60,17 +61,25 @@ CB_HD V3 normalizeGeneric(V3 v, float x) {
 // operator sequences with their slow-path calls cost instruction-cache space in the hot loop
 static __device__ __noinline__ V3 normalizeOutOfRange(V3 v, float x) { return normalizeGeneric(v, x); }
 #endif
-CB_HD V3 normalize(V3 v) {
+// `odd`, when given (the persistent kernel's scatter half), replaces the per-call branch to the out-of-range path: the
+// fast sequence runs unconditionally, a squared length outside its range raises *odd, and the caller redoes the whole
+// step out of line for that lane (inFastNormalizeRange on the bit pattern: one subtract, one unsigned compare).
+CB_HD V3 normalize(V3 v, bool *odd = nullptr) {
     float const x = mag2(v);
 #ifdef __CUDA_ARCH__
-    if (!inFastNormalizeRange(x))
+    if (odd) {
+        constexpr uint32_t kLo = 0x2b800000u, kHi = 0x67800000u; // 2^-40, 2^80: inFastNormalizeRange
+        *odd = *odd | (__float_as_uint(x) - kLo > kHi - kLo);
+    } else if (!inFastNormalizeRange(x)) {
         return normalizeOutOfRange(v, x);
+    }
     float len, s; // same values as normalizeGeneric, bit for bit (exact_arith.cuh)
     sqrtAndReciprocalExactFast(x, len, s);
     if (isAlmostZero(len))
         return V3{0.0f, 0.0f, 0.0f};
     return v * V3{s, s, s};
 #else
+    (void)odd;
     return normalizeGeneric(v, x);
 #endif
 }
@@ -81,13 +90,13 @@ struct Basis {
 
 // Math.hpp:424-434.  `abs(N(1)) > 0.95` compares a float against a double literal; the smallest float above
 // 0.95 is also the smallest float above 0.95f, so the float comparison below decides identically.
-CB_HD Basis constructBasis(V3 N) {
+CB_HD Basis constructBasis(V3 N, bool *odd = nullptr) {
     V3 helper{0.0f, 1.0f, 0.0f};
     if (fabsf(N.y) > 0.95f)
         helper = V3{0.0f, 0.0f, 1.0f};
     Basis b;
     b.N = N;
-    b.T = normalize(cross(helper, N));
+    b.T = normalize(cross(helper, N), odd);
     b.B = cross(b.T, N);
     return b;
 }

@@ -209,9 +209,29 @@ __global__ void CB_PERSISTENT_BOUNDS
 //     org.xyz | t      dir.xyz | prim      thr.rgb | pixel      rad.rgb | sample << 8 | depth      x0 x1 x2 | prob
 // P, N and the material are re-derived from (org, dir, t, prim) when the record is popped, as in the wavefront shade
 // kernel.  No block barrier anywhere: the queue belongs to one warp (__syncwarp orders its lanes' accesses).
-constexpr uint32_t kQueueSlots = 64;  // a pop leaves fewer than 32 records, a push adds at most 32
+constexpr uint32_t kQueueSlots = 64;  // a pop leaves fewer than 32 records, a push adds at most 32 (scatterParkedSlow too)
 constexpr uint32_t kQueueChunks = 5;
 constexpr size_t kQueueBytesPerWarp = kQueueSlots * kQueueChunks * sizeof(float4);
+
+// The scatter half once more for a parked record whose fast normalisations left their range (math.cuh normalize with
+// `odd`): hit point, normal and BSDF step with the per-call range checks, read from and written back to the record's
+// queue slot (chunks 0..2: org, dir, thr), so nothing but the slot address crosses the call.  Rare and out of line.
+static __device__ __noinline__ void scatterParkedSlow(float4 *queue, uint32_t slot, const DevSphere *spheres,
+                                                      const uint32_t *sphereMaterial, uint32_t nSpheres,
+                                                      const DevPlane *planes, const DevMaterial *materials) {
+    constexpr uint32_t kSlots = 64;
+    float4 const q0 = queue[slot], q1 = queue[kSlots + slot], q2 = queue[2 * kSlots + slot], q4 = queue[4 * kSlots + slot];
+    V3 org{q0.x, q0.y, q0.z}, dir{q1.x, q1.y, q1.z};
+    RGBf thr{q2.x, q2.y, q2.z};
+    V3 P, N;
+    uint32_t material;
+    hitSurface(org, dir, q0.w, static_cast<int32_t>(__float_as_uint(q1.w)), spheres, sphereMaterial, nSpheres, planes, P, N,
+               material);
+    shadeScatter(materials[material], P, N, q4.w, q4.x, q4.y, q4.z, org, dir, thr);
+    queue[slot] = make_float4(org.x, org.y, org.z, q0.w);
+    queue[kSlots + slot] = make_float4(dir.x, dir.y, dir.z, q1.w);
+    queue[2 * kSlots + slot] = make_float4(thr.r, thr.g, thr.b, q2.w);
+}
 
 template <bool kGrid>
 __global__ void CB_PERSISTENT_BOUNDS
@@ -254,9 +274,17 @@ __global__ void CB_PERSISTENT_BOUNDS
                 depth = sd & 255u;
                 V3 P, N;
                 uint32_t material;
+                bool odd = false; // a normalisation outside the fast sequence's range: redo this record out of line
                 hitSurface(org, dir, q0.w, static_cast<int32_t>(__float_as_uint(q1.w)), sh.spheres, sh.sphereMaterial,
-                           scene.nSpheres, sh.planes, P, N, material);
-                shadeScatter(sh.materials[material], P, N, q4.w, q4.x, q4.y, q4.z, org, dir, thr);
+                           scene.nSpheres, sh.planes, P, N, material, &odd);
+                shadeScatter(sh.materials[material], P, N, q4.w, q4.x, q4.y, q4.z, org, dir, thr, &odd);
+                if (odd) {
+                    scatterParkedSlow(queue, slot, sh.spheres, sh.sphereMaterial, scene.nSpheres, sh.planes, sh.materials);
+                    float4 const r0 = queue[slot], r1 = queue[kQueueSlots + slot], r2 = queue[2 * kQueueSlots + slot];
+                    org = V3{r0.x, r0.y, r0.z};
+                    dir = V3{r1.x, r1.y, r1.z};
+                    thr = RGBf{r2.x, r2.y, r2.z};
+                }
                 alive = true;
             }
             parked = base;
