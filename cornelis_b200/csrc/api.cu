@@ -364,7 +364,7 @@ int applyAcceleration(cornelis_cuda_scene *s, int mode) {
     s->accelMode = mode;
     s->shape.sceneSmemBytes = smem;
     CB_CUDA(configureKernels(s->shape));
-    CB_CUDA(configurePersistent(s->shape, wantGrid, s->gridPersistent));
+    CB_CUDA(configurePersistent(s->shape, wantGrid, s->view.nSpheres, s->gridPersistent));
     return CORNELIS_OK;
 }
 

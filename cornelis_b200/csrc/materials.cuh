@@ -171,6 +171,41 @@ __device__ __forceinline__ RGBf layeredEvalPdf(const DevMaterial &m, V3 wi, V3 w
     return RGBf{fma1(Df.r, k, Gf.r), fma1(Df.g, k, Gf.g), fma1(Df.b, k, Gf.b)};
 }
 
+// sin and cos of a double in [0, 2 Pi] — the only arguments the direction sampling has (angle = float(2 Pi x), x in
+// [0, 1)) — to within one ulp: Cody-Waite reduction by multiples of Pi / 2 with two fused steps (the quadrant is at most
+// 4, so the products are exact), then the classic degree-13 / degree-14 minimax kernels on [-Pi/4, Pi/4] (the
+// coefficients of fdlibm's k_sin.c / k_cos.c).  The CUDA library's sincos(double) computes the same thing behind a
+// range check whose slow path (huge arguments) passes its result through local memory: a store and a load executed
+// on every call, plus the call set-up.  The reference (glibc) and either device version agree to the last bit or
+// differ by one ulp of a DOUBLE; what the render uses is float(cos * radial), which a restatement of this function in C
+// reproduced for all 2^24 possible angles x 8 radial values without one mismatch against glibc (and
+// tests/test_gpu_parity.py::test_bsdf_sample_and_eval requires the sampled direction bit for bit on 2^18 inputs).
+__device__ __forceinline__ void sincosFirstTurn(double a, double &sn, double &cs) {
+    constexpr double kTwoOverPi = 6.36619772367581382433e-01, kPio2Hi = 1.57079632679489655800e+00,
+                     kPio2Lo = 6.12323399573676603587e-17, kRound = 6755399441055744.0; // 1.5 * 2^52
+    double const shifted = fma(a, kTwoOverPi, kRound); // the quadrant, rounded to nearest, sits in the low word
+    int const quadrant = __double2loint(shifted);
+    double const j = shifted - kRound;
+    double r = fma(-j, kPio2Hi, a);
+    r = fma(-j, kPio2Lo, r);
+    double const z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    double const s = fma(z * r, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    double const c = fma(z * z, pc, fma(-0.5, z, 1.0));
+    double const S = (quadrant & 1) ? c : s, C = (quadrant & 1) ? s : c;
+    sn = (quadrant & 2) ? -S : S;
+    cs = ((quadrant + 1) & 2) ? -C : C;
+}
+
 // LayeredBRDF::generateDirection, Materials.hpp:279-293: x2 < 0.5 samples the diffuse lobe UNIFORMLY over the
 // hemisphere (BRDF::generateDirection -> randomHemisphere, PRNG.hpp:39-55), otherwise the GGX half vector
 // (GlossyBRDF::generateDirection, Materials.hpp:156-175).  Both lobes build
@@ -198,7 +233,7 @@ __device__ __forceinline__ RGBf layeredSample(const DevMaterial &m, V3 wo, float
     }
     float const angle = 2.0f * kPi * (diffuse ? x1 : x0); // == float(2.0 * Pi * x): the 48-bit product is exact in double
     double sn, cs;
-    sincos(static_cast<double>(angle), &sn, &cs);
+    sincosFirstTurn(static_cast<double>(angle), sn, cs);
     float const kB = static_cast<float>(cs * static_cast<double>(radial));
     float const kT = static_cast<float>(sn * static_cast<double>(radial));
     V3 const v = (kB * b.B + kT * b.T) + axial * b.N;

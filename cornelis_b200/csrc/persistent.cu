@@ -40,9 +40,19 @@ constexpr unsigned long long kMaxClaim = 1024; // camera paths a warp claims per
 #ifndef CORNELIS_PERSISTENT_MIN_BLOCKS
 #define CORNELIS_PERSISTENT_MIN_BLOCKS 7
 #endif
+// Spheres whose discriminants are formed back to back before one vote decides whether any lane has a root among them
+// (geometry.cuh scanSpheres); 1 = one sphere per loop trip.
+#ifndef CORNELIS_RENDER_SPHERE_GROUP
+#define CORNELIS_RENDER_SPHERE_GROUP 4
+#endif
+// The queued kernel's sphere scan: scalar, or two spheres per FFMA2 (packed FP32) from a paired copy of the table.
+#ifndef CORNELIS_RENDER_PACKED
+#define CORNELIS_RENDER_PACKED 0
+#endif
 #ifndef CORNELIS_PERSISTENT_THREADS
 #define CORNELIS_PERSISTENT_THREADS 128
 #endif
+constexpr int kRenderScan = (CORNELIS_RENDER_PACKED && CORNELIS_RENDER_SPHERE_GROUP > 1) ? kScanPacked : kScanScalar;
 constexpr int kPersistentThreads = CORNELIS_PERSISTENT_THREADS; // CTA size of the persistent kernels
 constexpr int kPersistentWarps = kPersistentThreads / 32;
 // Register budget: either a minimum number of resident CTAs (ptxas derives the cap) or an explicit cap
@@ -144,7 +154,7 @@ __global__ void CB_PERSISTENT_BOUNDS
         // ---- intersect (Render.cpp:110-150) ----
         float t = INFINITY; // IntersectionData::reset, Geometry.cpp:7-12
         int32_t prim = -1;
-        closestHitScene<kGrid>(alive, org, dir, sh, scene, t, prim);
+        closestHitScene<kGrid, CORNELIS_RENDER_SPHERE_GROUP>(alive, org, dir, sh, scene, t, prim);
 
         // ---- accumulateAndBounce (Render.cpp:167-218) ----
         bool finished = false;
@@ -237,9 +247,14 @@ template <bool kGrid>
 __global__ void CB_PERSISTENT_BOUNDS
     k_persistent_queued(RenderConfig cfg, SceneView scene, unsigned long long *__restrict__ cursor,
                         unsigned long long limit, float4 *__restrict__ accum, float4 *__restrict__ accum2,
-                        bool dropNonFinite, Control *__restrict__ ctl, uint32_t queueOffset) {
+                        bool dropNonFinite, Control *__restrict__ ctl, uint32_t queueOffset, uint32_t pairsOffset,
+                        PackedConstants neutral) {
     extern __shared__ __align__(16) unsigned char smem[];
     SharedScene const sh = stageScene<kGrid>(scene, smem, true);
+    // pairsOffset != 0: the sphere table once more as pairs behind the queues, for the packed-FP32 scan (geometry.cuh)
+    float4 *const pairs = (!kGrid && pairsOffset) ? reinterpret_cast<float4 *>(smem + pairsOffset) : nullptr;
+    if (pairs)
+        stageSpherePairs(sh, scene.nSpheres, pairs);
     constexpr unsigned kFull = 0xffffffffu;
     unsigned const lane = threadIdx.x & 31u;
     unsigned const below = (1u << lane) - 1u;
@@ -340,7 +355,7 @@ __global__ void CB_PERSISTENT_BOUNDS
         // ---- intersect (Render.cpp:110-150) ----
         float t = INFINITY; // IntersectionData::reset, Geometry.cpp:7-12
         int32_t prim = -1;
-        closestHitScene<kGrid>(alive, org, dir, sh, scene, t, prim);
+        closestHitScene<kGrid, CORNELIS_RENDER_SPHERE_GROUP, kRenderScan>(alive, org, dir, sh, scene, t, prim, pairs, neutral);
 
         // ---- first half of accumulateAndBounce (Render.cpp:174-192): emission, Russian roulette ----
         bool finished = false, park = false;
@@ -404,6 +419,8 @@ __global__ void CB_PERSISTENT_BOUNDS
     }
 }
 
+static bool packedRenderScan() { return kRenderScan == kScanPacked; }
+
 static bool queuedVariant() {
     if (const char *env = std::getenv("CORNELIS_PERSISTENT_QUEUE"))
         return std::atoi(env) != 0;
@@ -411,13 +428,25 @@ static bool queuedVariant() {
 }
 
 template <bool kGrid>
-static cudaError_t configureOne(LaunchShape &shape, int &grid) {
+static cudaError_t configureOne(LaunchShape &shape, uint32_t nSpheres, int &grid) {
     cudaError_t e;
     // the queued variant appends one queue per warp to the staged scene tables; scenes whose tables leave no room for
     // the queues (close to the 227 KB carve-out) keep the lane-refill variant
     size_t const queueOffset = (shape.sceneSmemBytes + 15u) & ~static_cast<size_t>(15u);
-    size_t const queuedBytes = queueOffset + kPersistentWarps * kQueueBytesPerWarp;
+    size_t queuedBytes = queueOffset + kPersistentWarps * kQueueBytesPerWarp;
     shape.persistentQueued = queuedVariant() && queuedBytes <= shape.smemOptin;
+    shape.persistentPairsOffset = 0;
+    if (shape.persistentQueued && !kGrid && packedRenderScan() && nSpheres >= 2u) {
+        // the packed scan reads the paired table unconditionally: without room for it the lane-refill kernel (scalar
+        // scan) renders the scene
+        size_t const withPairs = queuedBytes + sizeof(float4) * (nSpheres & ~1u);
+        if (withPairs <= shape.smemOptin) {
+            shape.persistentPairsOffset = static_cast<uint32_t>(queuedBytes);
+            queuedBytes = withPairs;
+        } else {
+            shape.persistentQueued = false;
+        }
+    }
     shape.persistentSmemBytes = shape.persistentQueued ? queuedBytes : shape.sceneSmemBytes;
     shape.persistentQueueOffset = static_cast<uint32_t>(queueOffset);
     auto kernel = shape.persistentQueued ? reinterpret_cast<const void *>(k_persistent_queued<kGrid>)
@@ -458,8 +487,8 @@ uint32_t persistentClaim(unsigned long long paths, int grid) {
     return static_cast<uint32_t>(claim);
 }
 
-cudaError_t configurePersistent(LaunchShape &shape, bool gridScene, int &grid) {
-    return gridScene ? configureOne<true>(shape, grid) : configureOne<false>(shape, grid);
+cudaError_t configurePersistent(LaunchShape &shape, bool gridScene, uint32_t nSpheres, int &grid) {
+    return gridScene ? configureOne<true>(shape, nSpheres, grid) : configureOne<false>(shape, nSpheres, grid);
 }
 
 void launchPersistent(cudaStream_t s, const LaunchShape &shape, int grid, const RenderConfig &cfg, const SceneView &scene,
@@ -469,10 +498,12 @@ void launchPersistent(cudaStream_t s, const LaunchShape &shape, int grid, const 
     if (shape.persistentQueued) {
         if (scene.grid.enabled)
             k_persistent_queued<true><<<grid, kPersistentThreads, smem, s>>>(cfg, scene, cursor, limit, accum, accum2,
-                                                                        dropNonFinite, ctl, shape.persistentQueueOffset);
+                                                                        dropNonFinite, ctl, shape.persistentQueueOffset,
+                                                                        shape.persistentPairsOffset, hostPackedConstants());
         else
             k_persistent_queued<false><<<grid, kPersistentThreads, smem, s>>>(cfg, scene, cursor, limit, accum, accum2,
-                                                                         dropNonFinite, ctl, shape.persistentQueueOffset);
+                                                                         dropNonFinite, ctl, shape.persistentQueueOffset,
+                                                                         shape.persistentPairsOffset, hostPackedConstants());
     } else if (scene.grid.enabled) {
         k_persistent<true><<<grid, kPersistentThreads, smem, s>>>(cfg, scene, cursor, limit, accum, accum2, dropNonFinite, ctl);
     } else {

@@ -23,13 +23,14 @@ struct LaunchShape {
     bool persistentQueued = true;
     size_t persistentSmemBytes = 0;
     uint32_t persistentQueueOffset = 0;
+    uint32_t persistentPairsOffset = 0; // 0: no paired sphere table (scalar scan)
 };
 
 // Opts the kernels in to the scene's shared-memory size and fills the persistent grid sizes.
 cudaError_t configureKernels(LaunchShape &shape);
 
 // persistent-thread pipeline (persistent.cu)
-cudaError_t configurePersistent(LaunchShape &shape, bool gridScene, int &grid);
+cudaError_t configurePersistent(LaunchShape &shape, bool gridScene, uint32_t nSpheres, int &grid);
 uint32_t persistentClaim(unsigned long long paths, int grid); // RenderConfig::claim for a launch over `paths` camera paths
 void launchPersistent(cudaStream_t s, const LaunchShape &shape, int grid, const RenderConfig &cfg, const SceneView &scene,
                       unsigned long long *cursor, unsigned long long limit, float4 *accum, float4 *accum2,
