@@ -296,7 +296,7 @@ static void testRenderSession(int devices) {
     // time budget: samplesAA is only the upper limit; the image holds samplesPerPixel samples and is an unbiased
     // estimate of the same picture
     RenderOptions timed = o;
-    timed.samplesAA = 1 << 20;
+    timed.samplesAA = 1 << 23; // far more than any number of B200s renders of this frame in the budget (2 GPUs reach 2^20)
     timed.timeBudgetSeconds = 0.15;
     timed.saveImage = false;
     timed.dropNonFinite = true; // half a million spp meet the reference's NaN (|w.z| > 1 in Oren-Nayar) a few times
@@ -305,7 +305,7 @@ static void testRenderSession(int devices) {
     budgeted.render();
     double const took = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     auto const &bs = budgeted.statistics();
-    CHECK(bs.samplesPerPixel >= devices && bs.samplesPerPixel < (1 << 20) && bs.slices >= 2);
+    CHECK(bs.samplesPerPixel >= devices && bs.samplesPerPixel < (1 << 23) && bs.slices >= 2);
     CHECK(bs.pixelSamples == 96ull * 64ull * static_cast<unsigned long long>(bs.samplesPerPixel));
     CHECK(took < 1.0);
     double sumBudgeted = 0;
