@@ -977,6 +977,10 @@ int cornelis_cuda_intersect_compact(cornelis_cuda_scene *s, size_t n, const floa
     CB_CUDA(cudaMemcpyAsync(s->pool[0][3].ptr, state.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s->stream));
     Control init{};
     init.nIn = static_cast<uint32_t>(n);
+    // grid scenes: the first half of the batch plays the survivors of a previous pass (k_walk's pull model), the second
+    // half this pass's new camera rays (its packet phase), as k_plan would have laid them out
+    init.genBase = static_cast<uint32_t>(n / 2);
+    init.walkCursorCamera = n / 2;
     *s->hostControl = init;
     CB_CUDA(cudaMemcpyAsync(s->control.ptr, s->hostControl, sizeof(Control), cudaMemcpyHostToDevice, s->stream));
     launchIntersect(s->stream, s->shape, s->control.ptr, s->view, poolView(s, 0), s->hits.ptr, s->hitQueue.ptr,

@@ -150,6 +150,7 @@ struct Control {
     unsigned long long iterations; // passes
     unsigned long long contributions; // finished paths added to the framebuffer
     unsigned long long walkCursor;    // grid scenes: next pooled ray to be claimed by k_walk (reset by k_plan)
+    unsigned long long walkCursorCamera; // ... and the next of this pass's NEW camera rays [genBase, nIn) (reset by k_plan)
 };
 
 struct RenderConfig {

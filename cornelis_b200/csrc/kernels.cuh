@@ -17,6 +17,7 @@
 
 #include "device_types.h"
 #include "geometry.cuh"
+#include "geometry2.cuh"
 #include "materials.cuh"
 #include "math.cuh"
 #include "rng.cuh"
@@ -92,6 +93,25 @@ __device__ __forceinline__ void stageSpherePairs(const SharedScene &sh, uint32_t
         pairs[2u * p + 1u] = make_float4(a.z, b.z, a.w, b.w);
     }
     __syncthreads();
+}
+
+// The tables of closestHit2 (geometry2.cuh SplattedScene) built from a staged scene: every value twice.
+__device__ __forceinline__ SplattedScene stageSplatted(const SharedScene &sh, const SceneView &scene, float4 *dst) {
+    const float4 *spheres4 = reinterpret_cast<const float4 *>(sh.spheres);
+    for (uint32_t k = threadIdx.x; k < scene.nSpheres; k += blockDim.x) {
+        float4 const s = spheres4[k];
+        dst[2u * k] = make_float4(s.x, s.x, s.y, s.y);
+        dst[2u * k + 1u] = make_float4(s.z, s.z, s.w, s.w);
+    }
+    float4 *planes = dst + 2u * scene.nSpheres;
+    for (uint32_t k = threadIdx.x; k < scene.planeEnd[2]; k += blockDim.x) {
+        float4 const a = sh.axisPlanes[2u * k], b = sh.axisPlanes[2u * k + 1u]; // (p0k, p0T, p0B, w/2) (h/2, id, -, -)
+        planes[3u * k] = make_float4(a.x, a.x, a.y, a.y);
+        planes[3u * k + 1u] = make_float4(a.z, a.z, a.w, a.w);
+        planes[3u * k + 2u] = make_float4(b.x, b.x, b.y, 0.0f);
+    }
+    __syncthreads();
+    return SplattedScene{dst, planes};
 }
 
 // ------------------------------------------------------------------------------------------------ compaction --

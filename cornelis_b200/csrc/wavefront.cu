@@ -24,6 +24,7 @@ __global__ void k_plan(Control *ctl, RenderConfig cfg) {
     ctl->nHit = 0;
     ctl->nFinished = 0;
     ctl->walkCursor = 0;
+    ctl->walkCursorCamera = survivors;
     ctl->rays += survivors + gen;
     ctl->iterations += (survivors + gen) ? 1 : 0;
 }
@@ -113,6 +114,10 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_INTERSECT_MIN_BLOCKS) 
 // idle — because setting up a walk (plane tests, clipping, DDA) is itself ~150 instructions.  Only the hit records are
 // written here; k_compact_hits builds the queues (compaction #1) in a streaming pass.
 constexpr unsigned kWalkClaim = 256;  // rays a warp claims per atomic
+#ifndef CORNELIS_WALK_CAMERA_PHASE
+#define CORNELIS_WALK_CAMERA_PHASE 1
+#endif
+constexpr unsigned kWalkCameraClaim = 128; // camera rays a warp claims per atomic in phase 1: four coherent packets
 #ifndef CORNELIS_WALK_REFILL
 #define CORNELIS_WALK_REFILL 8
 #endif
@@ -129,14 +134,67 @@ constexpr unsigned kWalkTestCost = CORNELIS_WALK_TEST_COST, kWalkAdvanceCost = C
 #ifndef CORNELIS_WALK_MIN_BLOCKS
 #define CORNELIS_WALK_MIN_BLOCKS 4
 #endif
-__global__ void __launch_bounds__(kBlockThreads, CORNELIS_WALK_MIN_BLOCKS)
-    k_walk(Control *ctl, SceneView scene, PathPool pool, HitRecord *__restrict__ hits) {
+// kRangesInShared: the CTA is one of 1024 threads per SM and carries the cells' reference ranges in shared memory
+// (nCells + 1 prefix offsets, up to ~200 KB) behind the staged scene tables.  ncu on the 256-thread form showed the
+// walker waiting on memory, not issuing (long scoreboard 3.4 of 10.8 cycles per issue, issue slots 69 % busy, L1 hit
+// rate 39 %): every cell crossing is a dependent load of the cell's range, then of its references.  The first of the two
+// becomes a shared-memory access.  Same warps per SM either way (32: 62 registers).  Measured: no gain (1439 against
+// 1488 Msamples/s on config 4) — the references and the spheres behind them are the loads that matter, and they stay
+// where they were.  Off by default (LaunchShape::walkRangesInShared).
+constexpr int kWalkSharedThreads = 1024;
+template <bool kRangesInShared>
+__device__ __forceinline__ void walkBody(Control *ctl, const SceneView &scene, const PathPool &pool,
+                                         HitRecord *__restrict__ hits, uint32_t rangesOffset) {
     extern __shared__ __align__(16) unsigned char smem[];
     SharedScene const sh = stageScene<true>(scene, smem, false);
+    const uint32_t *cellStart = nullptr;
+    if (kRangesInShared) {
+        uint32_t *const dst = reinterpret_cast<uint32_t *>(smem + rangesOffset);
+        uint32_t const nCells = scene.grid.nx * scene.grid.ny * scene.grid.nz;
+        for (uint32_t c = threadIdx.x; c < nCells; c += blockDim.x)
+            dst[c] = scene.grid.cellRange[c].x;
+        if (threadIdx.x == 0)
+            dst[nCells] = scene.grid.cellRange[nCells - 1u].y; // ranges are consecutive: the prefix sums of the builder
+        __syncthreads();
+        cellStart = dst;
+    }
     constexpr unsigned kFull = 0xffffffffu;
     unsigned const lane = threadIdx.x & 31u;
     unsigned const below = (1u << lane) - 1u;
+    // Phase 1: this pass's NEW camera rays, [genBase, nIn) of the pool (k_plan puts them behind the survivors).  A warp's
+    // 32 consecutive camera paths are 32 consecutive pixels of one sample index: they cross nearly the same cells and
+    // test the same spheres, so one ray per lane walked to completion keeps the lanes together WITHOUT the per-round
+    // votes and refills of the pull model below (28 % of its instructions) and runs the set-up at full width
+    // (9.5 lanes there).  CORNELIS_WALK_CAMERA_PHASE=0 at build time sends every ray through the pull model.
+#if CORNELIS_WALK_CAMERA_PHASE
+    {
+        unsigned long long const cameraEnd = ctl->nIn;
+        for (;;) {
+            unsigned long long first = 0;
+            if (lane == 0)
+                first = atomicAdd(&ctl->walkCursorCamera, static_cast<unsigned long long>(kWalkCameraClaim));
+            first = __shfl_sync(kFull, first, 0);
+            if (first >= cameraEnd)
+                break;
+#pragma unroll 1
+            for (unsigned k = 0; k < kWalkCameraClaim; k += 32u) {
+                unsigned long long const mine = first + k + lane;
+                if (mine < cameraEnd) {
+                    uint32_t const at = static_cast<uint32_t>(mine);
+                    float4 const o4 = pool.org[at], d4 = pool.dir[at];
+                    float tc = INFINITY; // IntersectionData::reset, Geometry.cpp:7-12
+                    int32_t pc = -1;
+                    closestHitGrid(true, V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, scene, sh.planes, tc, pc, nullptr,
+                                   cellStart);
+                    hits[at] = HitRecord{tc, pc};
+                }
+            }
+        }
+    }
+    unsigned long long const n = ctl->genBase; // phase 2: the survivors of the last pass, [0, genBase)
+#else
     unsigned long long const n = ctl->nIn;
+#endif
     unsigned long long stashNext = 0, stashEnd = 0;
     bool walking = false, exhausted = false;
     uint32_t index = 0;
@@ -174,7 +232,7 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_WALK_MIN_BLOCKS)
                     d = V3{d4.x, d4.y, d4.z};
                     t = INFINITY; // IntersectionData::reset, Geometry.cpp:7-12
                     prim = -1;
-                    walking = gridWalkBegin(w, o, d, scene, sh.planes, t, prim);
+                    walking = gridWalkBegin(w, o, d, scene, sh.planes, t, prim, nullptr, cellStart);
                     if (!walking)
                         hits[index] = HitRecord{t, prim}; // decided without a walk (degenerate, outside the grid, ...)
                 }
@@ -197,7 +255,7 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_WALK_MIN_BLOCKS)
                 break;
             if (nAdvance * kWalkTestCost >= nTest * kWalkAdvanceCost) {
                 if (wantAdvance) {
-                    walking = gridWalkAdvance(w, scene.grid, t);
+                    walking = gridWalkAdvance(w, scene.grid, t, nullptr, cellStart);
                     if (!walking)
                         hits[index] = HitRecord{t, prim};
                 }
@@ -208,6 +266,16 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_WALK_MIN_BLOCKS)
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(kBlockThreads, CORNELIS_WALK_MIN_BLOCKS)
+    k_walk(Control *ctl, SceneView scene, PathPool pool, HitRecord *__restrict__ hits) {
+    walkBody<false>(ctl, scene, pool, hits, 0u);
+}
+
+__global__ void __launch_bounds__(kWalkSharedThreads, 1)
+    k_walk_shared(Control *ctl, SceneView scene, PathPool pool, HitRecord *__restrict__ hits, uint32_t rangesOffset) {
+    walkBody<true>(ctl, scene, pool, hits, rangesOffset);
 }
 
 // Compaction #1 for grid scenes (Render.cpp:142-149): hits to the hit queue, misses that carry radiance to the finished
@@ -445,6 +513,36 @@ __global__ void __launch_bounds__(kBlockThreads) k_intersect_batch(SceneView sce
     }
 }
 
+// The same on closestHit2 (geometry2.cuh): two rays per thread — ray i and ray i + ceil(n / 2) — on packed FP32.  What
+// the render kernel's pair mode runs, exposed here so that the parity tests of the intersect stage cover it
+// (CORNELIS_BATCH_PAIRS=1 routes cornelis_cuda_intersect(_device) through it; scenes scanned from shared memory only).
+__global__ void __launch_bounds__(kBlockThreads) k_intersect_batch2(SceneView scene, size_t n,
+                                                                    const float4 *__restrict__ org,
+                                                                    const float4 *__restrict__ dir,
+                                                                    HitRecord *__restrict__ hits, uint32_t splatOffset,
+                                                                    PackedConstants neutral) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SharedScene const sh = stageScene<false>(scene, smem, false);
+    SplattedScene const splat = stageSplatted(sh, scene, reinterpret_cast<float4 *>(smem + splatOffset));
+    size_t const half = (n + 1) / 2;
+    for (size_t base = static_cast<size_t>(blockIdx.x) * blockDim.x; base < half;
+         base += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        size_t const a = base + threadIdx.x, b = a + half;
+        bool const liveA = a < half, liveB = liveA && b < n;
+        float4 const zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 const oa = liveA ? org[a] : zero, da = liveA ? dir[a] : zero;
+        float4 const ob = liveB ? org[b] : zero, db = liveB ? dir[b] : zero;
+        float tA, tB;
+        int32_t primA, primB;
+        closestHit2(liveA, liveB, V3{oa.x, oa.y, oa.z}, V3{da.x, da.y, da.z}, V3{ob.x, ob.y, ob.z}, V3{db.x, db.y, db.z}, sh,
+                    splat, scene, neutral, tA, primA, tB, primB);
+        if (liveA)
+            hits[a] = HitRecord{tA, primA};
+        if (liveB)
+            hits[b] = HitRecord{tB, primB};
+    }
+}
+
 // Expands hit records into the reference's IntersectionData fields (P, N, MaterialId; Geometry.hpp:7-15).
 template <bool kGrid>
 __global__ void __launch_bounds__(kBlockThreads) k_hit_surface(SceneView scene, size_t n,
@@ -633,7 +731,15 @@ void launchIntersect(cudaStream_t s, const LaunchShape &shape, Control *ctl, con
                      const PathPool &pool, HitRecord *hits, uint32_t *hitQueue, FinishedPath *finished) {
     if (scene.grid.enabled) {
         if (shape.walkPull) {
-            k_walk<<<shape.gridWalk, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, scene, pool, hits);
+            // the cells' ranges ride in shared memory when they fit behind the scene tables (one 1024-thread CTA per SM)
+            size_t const rangesOffset = (shape.sceneSmemBytes + 15u) & ~static_cast<size_t>(15u);
+            size_t const nCells = static_cast<size_t>(scene.grid.nx) * scene.grid.ny * scene.grid.nz;
+            size_t const withRanges = rangesOffset + sizeof(uint32_t) * (nCells + 1u);
+            if (shape.walkRangesInShared && withRanges + 1024u <= shape.smemOptin)
+                k_walk_shared<<<shape.numSMs, kWalkSharedThreads, withRanges, s>>>(ctl, scene, pool, hits,
+                                                                                 static_cast<uint32_t>(rangesOffset));
+            else
+                k_walk<<<shape.gridWalk, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, scene, pool, hits);
             k_compact_hits<<<shape.gridAccumulate, kBlockThreads, 0, s>>>(ctl, pool, hits, hitQueue, finished);
         } else {
             k_intersect<true><<<shape.gridIntersectGrid, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, scene, pool, hits,
@@ -694,8 +800,22 @@ void launchIntersectBatch(cudaStream_t s, const LaunchShape &shape, const SceneV
             scene, n, org, dir, hits, 0u, hostPackedConstants());
         return;
     }
-    // the exhaustive scan runs on packed FP32 when the paired copy of the sphere table fits behind the staged scene
     size_t const pairOffset = (shape.sceneSmemBytes + 15u) & ~static_cast<size_t>(15u);
+    if (const char *env = std::getenv("CORNELIS_BATCH_PAIRS")) {
+        size_t const withSplat = pairOffset + splattedBytes(scene.nSpheres, scene.planeEnd[2]);
+        if (std::atoi(env) != 0 && withSplat <= shape.smemOptin) {
+            static bool optedIn = false;
+            if (!optedIn) {
+                cudaFuncSetAttribute(k_intersect_batch2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(shape.smemOptin));
+                optedIn = true;
+            }
+            k_intersect_batch2<<<gridFor((n + 1) / 2, shape.numSMs, shape.blocksPerSM), kBlockThreads, withSplat, s>>>(
+                scene, n, org, dir, hits, static_cast<uint32_t>(pairOffset), hostPackedConstants());
+            return;
+        }
+    }
+    // the exhaustive scan runs on packed FP32 when the paired copy of the sphere table fits behind the staged scene
     size_t const withPairs = pairOffset + sizeof(float4) * (scene.nSpheres & ~1u);
     bool const packed = shape.batchPacked && scene.nSpheres >= 2u && withPairs <= shape.smemOptin;
     k_intersect_batch<false><<<gridFor(n, shape.numSMs, shape.blocksPerSM), kBlockThreads,
@@ -761,6 +881,7 @@ cudaError_t configureKernels(LaunchShape &shape) {
         const void *staging[] = {reinterpret_cast<const void *>(k_intersect<false>),
                                  reinterpret_cast<const void *>(k_intersect<true>),
                                  reinterpret_cast<const void *>(k_walk),
+                                 reinterpret_cast<const void *>(k_walk_shared),
                                  reinterpret_cast<const void *>(k_shade<false>),
                                  reinterpret_cast<const void *>(k_shade<true>),
                                  reinterpret_cast<const void *>(k_intersect_batch<false>),
@@ -799,6 +920,8 @@ cudaError_t configureKernels(LaunchShape &shape) {
         return e;
     if (const char *env = std::getenv("CORNELIS_WALK_PULL"))
         shape.walkPull = std::atoi(env) != 0;
+    if (const char *env = std::getenv("CORNELIS_WALK_SHARED_RANGES"))
+        shape.walkRangesInShared = std::atoi(env) != 0;
     if ((e = resident(k_shade<false>, shape.sceneSmemBytes, shape.gridShade)) != cudaSuccess)
         return e;
     return resident(k_accumulate, 0, shape.gridAccumulate);

@@ -16,6 +16,9 @@ struct LaunchShape {
     // is resident for the whole launch and the grid-stride loops split the pool evenly.
     int gridRaygen = 592, gridIntersect = 592, gridIntersectGrid = 592, gridWalk = 592, gridShade = 592, gridAccumulate = 592;
     bool walkPull = true;     // grid scenes: k_walk (warps pull rays) + k_compact_hits instead of one ray per thread
+    // k_walk_shared (1024-thread CTAs, cell ranges in shared memory): measured on config 4 and left off — 1439 against
+    // 1488 Msamples/s (profiles/r2_walk); CORNELIS_WALK_SHARED_RANGES=1 switches it on
+    bool walkRangesInShared = false;
     bool batchPacked = true;  // k_intersect_batch scans the spheres two at a time on packed FP32 (FFMA2)
     size_t sceneSmemBytes = 0;
     size_t smemOptin = 227 * 1024;        // largest dynamic shared memory a CTA may opt in to; queried at scene creation

@@ -280,6 +280,37 @@ def test_packed_fp32_scan_is_bit_identical(binding, oracle, monkeypatch):
         assert np.array_equal(got["prim"], ref["prim"]) and bit_equal(got["t"], ref["t"]), count
 
 
+def test_two_rays_per_lane_scan_is_bit_identical(binding, oracle, monkeypatch):
+    """closestHit2 (csrc/geometry2.cuh): two rays per lane, every FP32 operation of the fast paths issued once for the
+    pair as an FFMA2.  Through CORNELIS_BATCH_PAIRS=1 the intersect entry point runs it; hit ids and t must equal the
+    oracle's bit for bit — on the microbench scene, on the Cornell box (camera rays, rays that start ON walls and the
+    floor, degenerate directions) and on batches of odd length (the last ray has no partner)."""
+    monkeypatch.setenv("CORNELIS_BATCH_PAIRS", "1")
+    rng = np.random.default_rng(23)
+    flat = scenes.microbench_scene(1024)
+    sc, osc = binding.Scene(flat), oracle.scene(flat)
+    sc.set_acceleration(binding.ACCEL_NONE)
+    for n in ((1 << 18) + 1, 1, 2, 33):
+        org, dirs = scenes.microbench_rays(n)
+        a, b = sc.intersect(org, dirs, surface=False), osc.intersect(org, dirs)
+        assert np.array_equal(a["prim"], b["prim"]) and bit_equal(a["t"], b["t"]), n
+    flat = scenes.cornell_box()
+    sc, osc = binding.Scene(flat), oracle.scene(flat)
+    n = 1 << 18
+    o1, d1 = osc.camera_rays(rng.random(n // 2, dtype=np.float32), rng.random(n // 2, dtype=np.float32))
+    o2 = (rng.random((n // 2, 3), dtype=np.float32) * np.float32(500) + np.float32([-250, 20, -250])).astype(np.float32)
+    o2[::4, 1] = 0.0       # on the floor
+    o2[1::4, 0] = -275.0   # on the left wall
+    o2[2::8, 2] = 275.0    # on the back wall
+    d2 = unit(rng, n // 2)
+    d2[3::4099] = 0
+    d2[5::4099, 0] = np.float32(1e-6)  # a component below RayEpsilon: the warp leaves the fast path
+    org, dirs = np.concatenate([o1, o2]).astype(np.float32), np.concatenate([d1, d2]).astype(np.float32)
+    a, b = sc.intersect(org, dirs, surface=False), osc.intersect(org, dirs)
+    assert np.array_equal(a["prim"], b["prim"]) and bit_equal(a["t"], b["t"])
+    assert (a["t"] == 0).sum() > 1000  # zero-distance re-hits of the plane a ray starts on: the sign of zero included
+
+
 def test_rays_on_and_tangent_to_spheres(binding, oracle):
     """Zero numerators of the sphere test (Geometry.cpp:77-84): an origin exactly on a sphere (C == r^2), a direction
     perpendicular to the centre offset (B == 0), both at once (t = 0 from a zero discriminant) and exact tangents.
