@@ -14,7 +14,8 @@ max-over-ranks of the timings.  The weak-scaling figure (every rank renders 4096
 "weak"; `--scaling weak` makes it the headline.
 
 At N = 1 the line also carries, under "configs", BASELINE.json configs[2] (the 2^24-ray intersection microbench) and
-configs[3] (the 10 000-sphere scene) with their own CPU baselines; at N > 1, under "single_process", a render of the
+configs[3] (the 10 000-sphere scene) with their own CPU baselines; at N > 1 configs[4] (3840x2160 at 16 384 spp split
+over the N GPUs, one timed render) and, under "single_process", a render of the
 same frame by ONE process driving all N GPUs through the C++ RenderSession (RenderOptions::devices = N, the CLI),
 compared with its own 1-GPU render.
 
@@ -431,6 +432,43 @@ def config4(args, device):
     return out
 
 
+def config5(world, rank, local_rank, comm, dist, torch, binding, flat_4k):
+    """BASELINE.json configs[4]: the Cornell scene at 3840x2160, 16 384 spp, sample-sharded across the GPUs of the box
+    with the NCCL framebuffer sum at the end — one timed render (all ranks; device time, max over ranks)."""
+    from cornelis_b200.sharding import sample_range
+    W, H, spp = 3840, 2160, 16384
+    first, count, total = sample_range(rank, world, spp, "strong")
+    scene = binding.Scene(flat_4k, device=local_rank)
+    stream = torch.cuda.Stream()
+    scene.set_stream(stream.cuda_stream)
+
+    def step(samples_first, samples_count):
+        with torch.cuda.stream(stream):
+            st = scene.render_accumulate(W, H, total, first_sample=samples_first, sample_count=samples_count)
+            comm.allreduce_framebuffers([scene])
+            scene.resolve_device(total)
+        return st
+
+    step(first, max(1, min(count, 16)))  # warm-up: allocations, the 133 MB all-reduce once
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    st = step(first, count)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=f"cuda:{local_rank}")
+    rays = torch.tensor([float(st["rays"])], dtype=torch.float64, device=f"cuda:{local_rank}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(rays, op=dist.ReduceOp.SUM)
+    scene.close()
+    seconds = float(t[0])
+    return {"workload": f"Cornell {W}x{H}, {spp} spp split over {world} GPUs by sample index, one ncclAllReduce of the "
+                        f"{W * H * 4} accumulator floats (BASELINE.json configs[4])",
+            "seconds": seconds, "msamples_per_s": float(W) * H * spp / seconds / 1e6,
+            "mrays_per_s": float(rays[0]) / seconds / 1e6, "spp_per_gpu": count, "steps": 1}
+
+
 def single_process_check(args, world):
     """The C++ path for one process driving several GPUs (RenderSession with RenderOptions::devices = N: one host
     thread per device, one grouped ncclReduce of the accumulation images onto device 0), through the CLI: the frame at
@@ -603,6 +641,14 @@ def ours(args, flat):
                  "ms_per_step": 1e3 * o_dev_s / o_steps, "steps": o_steps, "spp_in_image": o_spp,
                  "spp_per_gpu": o_spp // world}
 
+    c5 = None
+    if world > 1 and not args.no_configs:
+        from cornelis_b200 import scenes
+        try:
+            c5 = config5(world, rank, local_rank, comm, dist, torch, binding, scenes.cornell_box(aspect=2160 / 3840))
+        except Exception as e:  # every rank takes the same path: the collectives inside stay matched
+            c5 = {"error": f"{type(e).__name__}: {e}"}
+
     # whole-job totals: the ranks' sample ranges partition (strong) or extend (weak) the image's samples
     samples_per_step = float(npix) * total_spp
     rays_local = statistics.mean(s["rays"] for s in collected)
@@ -668,6 +714,8 @@ def ours(args, flat):
             except Exception as e:  # the headline line must still be printed
                 configs[name] = {"error": f"{type(e).__name__}: {e}"}
         line["configs"] = configs
+    if c5 is not None:
+        line["configs"] = {"c5": c5}
     if world > 1 and not args.no_single_process:
         try:
             line["single_process"] = single_process_check(args, world)

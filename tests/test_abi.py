@@ -74,6 +74,29 @@ def test_nccl_is_bound_at_run_time():
     assert "libnccl" not in needed
 
 
+def test_comm_entry_points_reject_bad_arguments():
+    """Argument checks of the exchange step that need no GPU."""
+    import torch
+    from cornelis_b200 import binding
+    L = binding.lib()
+    assert L.cornelis_cuda_comm_destroy(None) == 0  # like free(NULL)
+    assert L.cornelis_cuda_comm_info(None, None, None, None) == binding.ERR_INVALID_ARGUMENT
+    assert L.cornelis_cuda_allreduce_framebuffers(None, None, 0) == binding.ERR_INVALID_ARGUMENT
+    assert L.cornelis_cuda_reduce_framebuffers(None, 0) == binding.ERR_INVALID_ARGUMENT
+    assert L.cornelis_cuda_comm_unique_id(None) == binding.ERR_INVALID_ARGUMENT
+    with pytest.raises(ValueError):
+        binding.Comm.init_rank(b"short", 0, 1, 0)
+    uid = binding.comm_unique_id()
+    for rank, n in ((-1, 2), (2, 2), (0, 0)):
+        with pytest.raises(binding.CornelisError) as e:
+            binding.Comm.init_rank(uid, rank, n, 0)
+        assert e.value.code == binding.ERR_INVALID_ARGUMENT
+    if not torch.cuda.is_available():  # no device: the communicator of all GPUs has nothing to be made of
+        with pytest.raises(binding.CornelisError) as e:
+            binding.Comm.init_all([0])
+        assert e.value.code == binding.ERR_NO_DEVICE
+
+
 def test_product_does_not_touch_the_oracle():
     """Nothing under cornelis_b200/, include/, the host sources or tools/ may import, load or link oracle/ or read
     /root/reference: only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs do."""
