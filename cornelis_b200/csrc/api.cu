@@ -950,8 +950,8 @@ int cornelis_cuda_intersect_compact(cornelis_cuda_scene *s, size_t n, const floa
     *nHits = *nMisses = 0;
     if (n == 0)
         return CORNELIS_OK;
-    if (n > (1u << 28))
-        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "batch too large");
+    if (n > (1u << 26)) // 80 B of pool and queues per ray on the device, 32 B of staging on the host
+        return fail(CORNELIS_ERR_INVALID_ARGUMENT, "batch too large (at most 2^26 rays)");
     // the pool as a render pass would hold these rays: origin, direction, throughput 1, radiance (1, 0, 0) | ray index
     for (int a = 0; a < 4; a++)
         CB_CUDA(s->pool[0][a].reserve(n));

@@ -229,7 +229,7 @@ constexpr size_t kQueueBytesPerWarp = kQueueSlots * kQueueChunks * sizeof(float4
 static __device__ __noinline__ void scatterParkedSlow(float4 *queue, uint32_t slot, const DevSphere *spheres,
                                                       const uint32_t *sphereMaterial, uint32_t nSpheres,
                                                       const DevPlane *planes, const DevMaterial *materials) {
-    constexpr uint32_t kSlots = 64;
+    constexpr uint32_t kSlots = kQueueSlots;
     float4 const q0 = queue[slot], q1 = queue[kSlots + slot], q2 = queue[2 * kSlots + slot], q4 = queue[4 * kSlots + slot];
     V3 org{q0.x, q0.y, q0.z}, dir{q1.x, q1.y, q1.z};
     RGBf thr{q2.x, q2.y, q2.z};
