@@ -230,6 +230,36 @@ def test_general_planes_and_odd_rays(binding, oracle):
     assert (a["prim"] >= 9).any() and (a["prim"] == 3).any()
 
 
+def test_plane_tables_odd_cases(binding, oracle):
+    """The compact axis-plane table compares |e| with HALF the extents, which is exact only when the halving is: planes
+    with tiny, zero, infinite or NaN extents (the first is classified general at scene creation), scenes without planes
+    and scenes without spheres must all agree with the oracle bit for bit."""
+    rng = np.random.default_rng(91)
+    n = 100000
+    o = (rng.random((n, 3), dtype=np.float32) * 400 - 200).astype(np.float32)
+    d = unit(rng, n)
+    o[::7, 1] = -100.0  # origins on the first plane
+    base = scenes.cornell_box()
+    for extents in ([1e-38, 50.0], [0.0, 300.0], [np.inf, 120.0], [np.nan, 80.0], [3e-33, 3e-33], [250.0, np.inf]):
+        flat = dict(base)
+        flat["planes"] = np.array([[0, 1, 0, 0, -100, 0, extents[0], extents[1], 0],
+                                   [1, 0, 0, -150, 0, 0, 260, 260, 0],
+                                   [0, 0, -1, 0, 0, 150, extents[1], extents[0], 0]], np.float32)
+        flat["plane_mat"] = np.array([1, 2, 3], np.int32)
+        a, b = binding.Scene(flat).intersect(o, d), oracle.scene(flat).intersect(o, d)
+        assert np.array_equal(a["prim"], b["prim"]), extents
+        assert bit_equal(a["t"], b["t"]), extents
+    no_planes = dict(base)
+    no_planes["planes"], no_planes["plane_mat"] = np.zeros((0, 9), np.float32), np.zeros(0, np.int32)
+    no_spheres = dict(base)
+    no_spheres["spheres"], no_spheres["sphere_mat"] = np.zeros((0, 4), np.float32), np.zeros(0, np.int32)
+    for flat in (no_planes, no_spheres):
+        a, b = binding.Scene(flat).intersect(o, d), oracle.scene(flat).intersect(o, d)
+        assert np.array_equal(a["prim"], b["prim"]) and bit_equal(a["t"], b["t"])
+        img, st = binding.Scene(flat).render(32, 24, 8)
+        assert st["pixel_samples"] == 32 * 24 * 8 and img.shape == (24, 32, 3)
+
+
 def test_rays_starting_on_planes_keep_the_sign_of_zero(binding, oracle):
     """A bounce off a plane starts ON it about one time in four (o_k == p0_k after rounding): t against that plane is
     a signed zero whose sign the reference derives from -(diff . N) / (d . N).  The fast path must return the same
