@@ -217,7 +217,7 @@ __device__ __forceinline__ bool shadeRoulette(const DevMaterial &mat, uint32_t d
 // dir is the incoming ray's direction on entry and the sampled direction on exit.
 // `odd`: see normalize (math.cuh) — the caller redoes the step without it when it comes back raised.
 __device__ __forceinline__ void shadeScatter(const DevMaterial &mat, V3 P, V3 N, float prob, float x0, float x1, float x2,
-                                             V3 &org, V3 &dir, RGBf &thr, bool *odd = nullptr) {
+                                             V3 &org, V3 &dir, RGBf &thr, OddWatch *odd = nullptr) {
     V3 const wOut = -dir;                                                   // Render.cpp:174
     Basis const basis = constructBasis(N, odd);                             // Render.cpp:194
     V3 wIn;

@@ -38,15 +38,19 @@ constexpr float kHemispherePdf = 1.0f / (2.0f * kPi); // randomHemispherePDF(), 
 // TOLERANT tail: values that are only multiplied into the result (the reciprocal of base^2, Smith G, Fresnel,
 // tan = sin/cos, the Oren-Nayar factor, the final quotients) may be off by a couple of ulp; they use the
 // single-instruction MUFU approximations (<= 2 ulp each), keeping f and pdf within ~3e-6 of the reference against a
-// budget of 1e-5.
+// budget of 1e-5.  The .ftz forms: MUFU itself flushes subnormals, and without .ftz the compiler wraps every use in a
+// range test and two rescalings (seven instructions per reciprocal, four per square root — 4 % of the render kernel's
+// instructions, profiles/r2_ncu).  No operand of the tail is subnormal or above 2^126: the reciprocals are taken of
+// base^2 in [alpha^4, 1], of sums >= 1, of cosines the reference has already compared with its 5e-5 epsilon, of
+// pdf * prob >= 4e-3; the square roots of 1 - c^2 (0 or >= 2^-24) and of 1 + k^2.
 __device__ __forceinline__ float approxSqrt(float x) {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 __device__ __forceinline__ float approxRcp(float x) {
     float r;
-    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 __device__ __forceinline__ float approxDiv(float a, float b) { return a * approxRcp(b); } // (__fdividef adds range scaling)
@@ -104,6 +108,19 @@ __device__ __forceinline__ float shadowMaskingTR(float tanI, float tanO, float a
     return approxRcp(1.0f + lambdaTR(tanI, alpha) + lambdaTR(tanO, alpha));
 }
 
+// sqrtf(x) for x = 1 - c^2 with |c| <= 1, i.e. x == 0 or 2^-24 <= x <= 1: the exact fast sequence, straight-line (the
+// compiler's sqrtf carries a range test and a branch to an out-of-line call).  x < 0 or NaN (|c| > 1, NaN) gives NaN
+// like sqrtf; so would x == 0 (0 * rsqrt(0)), hence the select.
+__device__ __forceinline__ float sqrtUnitExact(float x) {
+    float const r = sqrtExactFast(x);
+    return x == 0.0f ? 0.0f : r;
+}
+// a / s for s = sqrtUnitExact(..) in [2^-12, 1] and |a| <= 1: RN(a / s) by the exact fast sequence for |a| >= 2^-80
+// and for a == 0.  A smaller non-zero a (a direction component below 1e-24) may come out one ulp off: its only use is
+// r * r and r * r' in cosD, where it vanishes against 1.  s == 0 or NaN gives NaN where the operator gives +-INF or
+// NaN; both make cosD NaN (INF * 0 and 1 - INF^2 under the root), which std::max(0, NaN) turns into 0.
+__device__ __forceinline__ float divideByUnitExact(float a, float s) { return divideExactFast0(a, s, rcpSeedRefined(s)); }
+
 // OrenNayarBRDF::operator(), Materials.hpp:211-228, without its seven transcendental calls.
 //
 // The reference takes the angles from WORLD-space components (cos theta = w.z, cos phi = w.x / sin theta — not
@@ -118,10 +135,10 @@ __device__ __forceinline__ float shadowMaskingTR(float tanI, float tanO, float a
 __device__ __forceinline__ RGBf orenNayarEval(const DevMaterial &m, V3 wi, V3 wo) {
     float cI = wi.z, cO = wo.z;
     // exact up to r: whether |r| exceeds 1 (-> NaN azimuth -> the b-term vanishes) is a discontinuity of size ~b
-    float sI = sqrtf(1.0f - cI * cI);
-    float sO = sqrtf(1.0f - cO * cO);
-    float rI = wi.x / sI;
-    float rO = wo.x / sO;
+    float sI = sqrtUnitExact(1.0f - cI * cI);
+    float sO = sqrtUnitExact(1.0f - cO * cO);
+    float rI = divideByUnitExact(wi.x, sI);
+    float rO = divideByUnitExact(wo.x, sO);
     // (the sign of 1 - r^2, hence the NaN that switches the b-term off, is the same fused or not: r^2 > 1 iff |r| > 1)
     float cosD = fma1(approxSqrt(fma1(-rI, rI, 1.0f)), approxSqrt(fma1(-rO, rO, 1.0f)), rI * rO);
     bool const thetaONaN = !(fabsf(cO) <= 1.0f);
@@ -132,7 +149,7 @@ __device__ __forceinline__ RGBf orenNayarEval(const DevMaterial &m, V3 wi, V3 wo
 
 // GlossyBRDF::operator() (Materials.hpp:130-154) and GlossyBRDF::pdf (Materials.hpp:177-188) share the half vector
 // h = normalize(wi + wo), its cosine and D; evaluated together.  Returns the scalar that multiplies the tint.
-__device__ __forceinline__ float glossyEvalPdf(const DevMaterial &m, V3 wi, V3 wo, V3 N, float &pdf, bool *odd = nullptr) {
+__device__ __forceinline__ float glossyEvalPdf(const DevMaterial &m, V3 wi, V3 wo, V3 N, float &pdf, OddWatch *odd = nullptr) {
     V3 const h = normalize(wi + wo, odd);                  // exact chain
     float const cosThetaH = stdMax(0.0f, dot(h, N));
     float D = 1.0f;
@@ -161,7 +178,7 @@ __device__ __forceinline__ float glossyEvalPdf(const DevMaterial &m, V3 wi, V3 w
 
 // LayeredBRDF::operator() and ::pdf (Materials.hpp:255-277): f = (1 - F(N.wi)) * diffuse + glossy;
 // pdf = 0.5 * (1/(2 Pi) + pdf_glossy) — the unweighted average whatever lobe was sampled.
-__device__ __forceinline__ RGBf layeredEvalPdf(const DevMaterial &m, V3 wi, V3 wo, V3 N, float &pdf, bool *odd = nullptr) {
+__device__ __forceinline__ RGBf layeredEvalPdf(const DevMaterial &m, V3 wi, V3 wo, V3 N, float &pdf, OddWatch *odd = nullptr) {
     float pdfGlossy;
     float const g = glossyEvalPdf(m, wi, wo, N, pdfGlossy, odd);
     pdf = fma1(0.5f, pdfGlossy, 0.5f * kHemispherePdf);
@@ -170,6 +187,17 @@ __device__ __forceinline__ RGBf layeredEvalPdf(const DevMaterial &m, V3 wi, V3 w
     float const k = 1.0f - schlick(stdMax(0.0f, dot(N, wi)), m.r0);
     return RGBf{fma1(Df.r, k, Gf.r), fma1(Df.g, k, Gf.g), fma1(Df.b, k, Gf.b)};
 }
+
+static __constant__ double kSinCos[16] = {
+    6.36619772367581382433e-01,  // 0: 2 / Pi
+    1.57079632679489655800e+00,  // 1: Pi / 2, high part
+    6.12323399573676603587e-17,  // 2: Pi / 2, low part
+    6755399441055744.0,          // 3: 1.5 * 2^52
+    1.58969099521155010221e-10,  -2.50507602534068634195e-08, 2.75573137070700676789e-06,  // 4..9: k_sin.c S6..S1
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03,  -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09,  -2.75573143513906633035e-07, // 10..15: k_cos.c C6..C1
+    2.48015872894767294178e-05,  -1.38888888888741095749e-03, 4.16666666666666019037e-02,
+};
 
 // sin and cos of a double in [0, 2 Pi] — the only arguments the direction sampling has (angle = float(2 Pi x), x in
 // [0, 1)) — to within one ulp: Cody-Waite reduction by multiples of Pi / 2 with two fused steps (the quadrant is at most
@@ -181,25 +209,26 @@ __device__ __forceinline__ RGBf layeredEvalPdf(const DevMaterial &m, V3 wi, V3 w
 // reproduced for all 2^24 possible angles x 8 radial values without one mismatch against glibc (and
 // tests/test_gpu_parity.py::test_bsdf_sample_and_eval requires the sampled direction bit for bit on 2^18 inputs).
 __device__ __forceinline__ void sincosFirstTurn(double a, double &sn, double &cs) {
-    constexpr double kTwoOverPi = 6.36619772367581382433e-01, kPio2Hi = 1.57079632679489655800e+00,
-                     kPio2Lo = 6.12323399573676603587e-17, kRound = 6755399441055744.0; // 1.5 * 2^52
-    double const shifted = fma(a, kTwoOverPi, kRound); // the quadrant, rounded to nearest, sits in the low word
+    // (the constants live in constant memory, kSinCos: a 64-bit immediate costs two UMOVs per use, a constant-bank
+    // operand none)
+    const double *const k = kSinCos;
+    double const shifted = fma(a, k[0], k[3]); // the quadrant, rounded to nearest, sits in the low word
     int const quadrant = __double2loint(shifted);
-    double const j = shifted - kRound;
-    double r = fma(-j, kPio2Hi, a);
-    r = fma(-j, kPio2Lo, r);
+    double const j = shifted - k[3];
+    double r = fma(-j, k[1], a);
+    r = fma(-j, k[2], r);
     double const z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
+    double ps = fma(z, k[4], k[5]);
+    ps = fma(z, ps, k[6]);
+    ps = fma(z, ps, k[7]);
+    ps = fma(z, ps, k[8]);
+    ps = fma(z, ps, k[9]);
     double const s = fma(z * r, ps, r);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
+    double pc = fma(z, k[10], k[11]);
+    pc = fma(z, pc, k[12]);
+    pc = fma(z, pc, k[13]);
+    pc = fma(z, pc, k[14]);
+    pc = fma(z, pc, k[15]);
     double const c = fma(z * z, pc, fma(-0.5, z, 1.0));
     double const S = (quadrant & 1) ? c : s, C = (quadrant & 1) ? s : c;
     sn = (quadrant & 2) ? -S : S;
@@ -218,7 +247,7 @@ __device__ __forceinline__ void sincosFirstTurn(double a, double &sn, double &cs
 // functions at the sampled wi.  If the half vector falls below the surface wi stays 0 (Materials.hpp:169-170).
 // `odd`: see normalize (math.cuh).
 __device__ __forceinline__ RGBf layeredSample(const DevMaterial &m, V3 wo, float x0, float x1, float x2,
-                                              const Basis &b, V3 &wi, float &pdf, bool *odd = nullptr) {
+                                              const Basis &b, V3 &wi, float &pdf, OddWatch *odd = nullptr) {
     bool const diffuse = x2 < 0.5f;
     float radial, axial;
     if (diffuse) {

@@ -62,14 +62,19 @@ CB_HD V3 normalizeGeneric(V3 v, float x) {
 static __device__ __noinline__ V3 normalizeOutOfRange(V3 v, float x) { return normalizeGeneric(v, x); }
 #endif
 // `odd`, when given (the persistent kernel's scatter half), replaces the per-call branch to the out-of-range path: the
-// fast sequence runs unconditionally, a squared length outside its range raises *odd, and the caller redoes the whole
-// step out of line for that lane (inFastNormalizeRange on the bit pattern: one subtract, one unsigned compare).
-CB_HD V3 normalize(V3 v, bool *odd = nullptr) {
+// fast sequence runs unconditionally and the caller redoes the whole step out of line for a lane whose squared length
+// was outside its range.  *odd accumulates the LARGEST (bits(x) - bits(2^-40)) seen, as unsigned: in range means at
+// most kNormalizeSpan, anything else (smaller, larger, negative, NaN) wraps or lands above it — one subtract and one
+// unsigned maximum per call, one compare per step (oddRaised).
+constexpr uint32_t kNormalizeLo = 0x2b800000u, kNormalizeSpan = 0x67800000u - 0x2b800000u; // 2^-40 .. 2^80
+typedef uint32_t OddWatch;
+CB_HD bool oddRaised(OddWatch w) { return w > kNormalizeSpan; }
+CB_HD V3 normalize(V3 v, OddWatch *odd = nullptr) {
     float const x = mag2(v);
 #ifdef __CUDA_ARCH__
     if (odd) {
-        constexpr uint32_t kLo = 0x2b800000u, kHi = 0x67800000u; // 2^-40, 2^80: inFastNormalizeRange
-        *odd = *odd | (__float_as_uint(x) - kLo > kHi - kLo);
+        uint32_t const excess = __float_as_uint(x) - kNormalizeLo; // inFastNormalizeRange on the bit pattern
+        *odd = *odd > excess ? *odd : excess;
     } else if (!inFastNormalizeRange(x)) {
         return normalizeOutOfRange(v, x);
     }
@@ -90,7 +95,7 @@ struct Basis {
 
 // Math.hpp:424-434.  `abs(N(1)) > 0.95` compares a float against a double literal; the smallest float above
 // 0.95 is also the smallest float above 0.95f, so the float comparison below decides identically.
-CB_HD Basis constructBasis(V3 N, bool *odd = nullptr) {
+CB_HD Basis constructBasis(V3 N, OddWatch *odd = nullptr) {
     V3 helper{0.0f, 1.0f, 0.0f};
     if (fabsf(N.y) > 0.95f)
         helper = V3{0.0f, 0.0f, 1.0f};

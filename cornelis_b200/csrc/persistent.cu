@@ -289,11 +289,11 @@ __global__ void CB_PERSISTENT_BOUNDS
                 depth = sd & 255u;
                 V3 P, N;
                 uint32_t material;
-                bool odd = false; // a normalisation outside the fast sequence's range: redo this record out of line
+                OddWatch odd = 0; // a normalisation outside the fast sequence's range: redo this record out of line
                 hitSurface(org, dir, q0.w, static_cast<int32_t>(__float_as_uint(q1.w)), sh.spheres, sh.sphereMaterial,
                            scene.nSpheres, sh.planes, P, N, material, &odd);
                 shadeScatter(sh.materials[material], P, N, q4.w, q4.x, q4.y, q4.z, org, dir, thr, &odd);
-                if (odd) {
+                if (oddRaised(odd)) {
                     scatterParkedSlow(queue, slot, sh.spheres, sh.sphereMaterial, scene.nSpheres, sh.planes, sh.materials);
                     float4 const r0 = queue[slot], r1 = queue[kQueueSlots + slot], r2 = queue[2 * kQueueSlots + slot];
                     org = V3{r0.x, r0.y, r0.z};
