@@ -37,8 +37,11 @@ constexpr unsigned long long kMaxClaim = 1024; // camera paths a warp claims per
 // rematerialisation — the same 2952 instructions at either budget; profiles/r2_persistent/variants.log):
 //   128 x 6 (78 registers, 24 warps) 7947     128 x 7 (64 registers) 8097     128 x 8 (64 registers, 32 warps/SM) 8240
 // A minimum of 7 CTAs per SM makes ptxas settle on 64 registers, and the occupancy calculator then finds room for 8.
+// Later in round 2 (a shorter loop after the SASS-level pass over the shading step; gpurun_out/r3b in the same log):
+//   __launch_bounds__(128, 7): 66 registers, 9404     (128, 6): 67 registers — still 7 CTAs per SM — and a schedule
+//   that runs at 9593
 #ifndef CORNELIS_PERSISTENT_MIN_BLOCKS
-#define CORNELIS_PERSISTENT_MIN_BLOCKS 7
+#define CORNELIS_PERSISTENT_MIN_BLOCKS 6
 #endif
 // Spheres whose discriminants are formed back to back before one vote decides whether any lane has a root among them
 // (geometry.cuh scanSpheres); 1 = one sphere per loop trip.
@@ -274,9 +277,12 @@ __global__ void CB_PERSISTENT_BOUNDS
         uint32_t pixel = 0, sample = 0, depth = 0;
         if (parked >= 32u || (!camerasLeft && parked != 0u)) {
             // ---- second half of accumulateAndBounce (Render.cpp:194-213) for a batch of parked survivors ----
+            // Every lane runs the step: a lane beyond the batch (only while the queue drains at the end of the run)
+            // repeats the batch's last record and is not alive afterwards.  No lane-dependent branch around the
+            // longest stretch of the loop, and no default values to set up for the lanes that would skip it.
             uint32_t const n = parked < 32u ? parked : 32u, base = parked - n;
-            if (lane < n) {
-                uint32_t const slot = base + lane;
+            {
+                uint32_t const slot = base + (lane < n ? lane : n - 1u);
                 float4 const q0 = queue[slot], q1 = queue[kQueueSlots + slot], q2 = queue[2 * kQueueSlots + slot],
                              q3 = queue[3 * kQueueSlots + slot], q4 = queue[4 * kQueueSlots + slot];
                 org = V3{q0.x, q0.y, q0.z};
@@ -300,7 +306,7 @@ __global__ void CB_PERSISTENT_BOUNDS
                     dir = V3{r1.x, r1.y, r1.z};
                     thr = RGBf{r2.x, r2.y, r2.z};
                 }
-                alive = true;
+                alive = lane < n;
             }
             parked = base;
             __syncwarp(); // the slots read here are overwritten by this iteration's pushes
