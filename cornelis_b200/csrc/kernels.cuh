@@ -73,14 +73,14 @@ __device__ __forceinline__ SharedScene stageScene(const SceneView &scene, unsign
 
 // The intersect stage for either scene representation.  kGrid is a template parameter of the kernels (the host picks
 // the instantiation from SceneView::grid.enabled) so the few-primitive kernels keep their register budget.
-template <bool kGrid, int kSphereUnroll = 1, int kPacked = kScanEither>
+template <bool kGrid, int kSphereUnroll = 1, int kPacked = kScanEither, bool kSettleZero = true>
 __device__ __forceinline__ void closestHitScene(bool live, V3 o, V3 d, const SharedScene &sh, const SceneView &scene,
                                                 float &tBest, int32_t &primBest, const float4 *pairs = nullptr,
                                                 PackedConstants neutral = PackedConstants{1.0f, -0.0f}) {
     if (kGrid)
         closestHitGrid(live, o, d, scene, sh.planes, tBest, primBest);
     else
-        closestHit<kSphereUnroll, kPacked>(live, o, d, sh, scene, tBest, primBest, pairs, neutral);
+        closestHit<kSphereUnroll, kPacked, kSettleZero>(live, o, d, sh, scene, tBest, primBest, pairs, neutral);
 }
 
 // The sphere table of a staged scene once more, as pairs for scanSpheresPacked (geometry.cuh):

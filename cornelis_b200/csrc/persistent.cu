@@ -157,7 +157,7 @@ __global__ void CB_PERSISTENT_BOUNDS
         // ---- intersect (Render.cpp:110-150) ----
         float t = INFINITY; // IntersectionData::reset, Geometry.cpp:7-12
         int32_t prim = -1;
-        closestHitScene<kGrid, CORNELIS_RENDER_SPHERE_GROUP>(alive, org, dir, sh, scene, t, prim);
+        closestHitScene<kGrid, CORNELIS_RENDER_SPHERE_GROUP, kScanEither, false>(alive, org, dir, sh, scene, t, prim);
 
         // ---- accumulateAndBounce (Render.cpp:167-218) ----
         bool finished = false;
@@ -361,7 +361,8 @@ __global__ void CB_PERSISTENT_BOUNDS
         // ---- intersect (Render.cpp:110-150) ----
         float t = INFINITY; // IntersectionData::reset, Geometry.cpp:7-12
         int32_t prim = -1;
-        closestHitScene<kGrid, CORNELIS_RENDER_SPHERE_GROUP, kRenderScan>(alive, org, dir, sh, scene, t, prim, pairs, neutral);
+        closestHitScene<kGrid, CORNELIS_RENDER_SPHERE_GROUP, kRenderScan, false>(alive, org, dir, sh, scene, t, prim, pairs,
+                                                                                 neutral);
 
         // ---- first half of accumulateAndBounce (Render.cpp:174-192): emission, Russian roulette ----
         bool finished = false, park = false;
