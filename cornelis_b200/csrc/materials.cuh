@@ -279,10 +279,10 @@ __device__ __forceinline__ RGBf layeredSample(const DevMaterial &m, V3 wo, float
 // russianRouletteFactor, Render.cpp:153-165.
 CB_HD float russianRouletteFactor(float tr, float tg, float tb, uint32_t depth) {
     constexpr float Base = 0.55f;
-    if (depth < 3)
-        return 0.99f;
-    float power = stdClamp(tr * tr + tg * tg + tb * tb, 0.05f / Base, 0.99f);
-    return Base * power;
+    // (one select instead of an early return: nearly every warp holds a path at depth >= 3, so a branch saves nothing)
+    float const power = stdClamp(tr * tr + tg * tg + tb * tb, 0.05f / Base, 0.99f);
+    float const deep = Base * power;
+    return depth < 3 ? 0.99f : deep;
 }
 
 // Host-side construction of the per-material constants, with the reference's constructor arithmetic

@@ -63,10 +63,12 @@ static __device__ __noinline__ V3 normalizeOutOfRange(V3 v, float x) { return no
 #endif
 // `odd`, when given (the persistent kernel's scatter half), replaces the per-call branch to the out-of-range path: the
 // fast sequence runs unconditionally and the caller redoes the whole step out of line for a lane whose squared length
-// was outside its range.  *odd accumulates the LARGEST (bits(x) - bits(2^-40)) seen, as unsigned: in range means at
+// was outside its range.  *odd accumulates the LARGEST (bits(x) - bits(2^-28)) seen, as unsigned: in range means at
 // most kNormalizeSpan, anything else (smaller, larger, negative, NaN) wraps or lands above it — one subtract and one
-// unsigned maximum per call, one compare per step (oddRaised).
-constexpr uint32_t kNormalizeLo = 0x2b800000u, kNormalizeSpan = 0x67800000u - 0x2b800000u; // 2^-40 .. 2^80
+// unsigned maximum per call, one compare per step (oddRaised).  The watched range starts at 2^-28 rather than at the
+// 2^-40 the fast sequence could take: from there up the length is at least 2^-14 > RayEpsilon, so the reference's
+// collapse of a short vector to zero (Math.hpp:394) cannot apply and the watched call does not test for it.
+constexpr uint32_t kNormalizeLo = 0x31800000u, kNormalizeSpan = 0x67800000u - 0x31800000u; // 2^-28 .. 2^80
 typedef uint32_t OddWatch;
 CB_HD bool oddRaised(OddWatch w) { return w > kNormalizeSpan; }
 CB_HD V3 normalize(V3 v, OddWatch *odd = nullptr) {
@@ -80,7 +82,7 @@ CB_HD V3 normalize(V3 v, OddWatch *odd = nullptr) {
     }
     float len, s; // same values as normalizeGeneric, bit for bit (exact_arith.cuh)
     sqrtAndReciprocalExactFast(x, len, s);
-    if (isAlmostZero(len))
+    if (!odd && isAlmostZero(len))
         return V3{0.0f, 0.0f, 0.0f};
     return v * V3{s, s, s};
 #else

@@ -365,27 +365,27 @@ __global__ void CB_PERSISTENT_BOUNDS
                                                                                  neutral);
 
         // ---- first half of accumulateAndBounce (Render.cpp:174-192): emission, Russian roulette ----
-        bool finished = false, park = false;
-        float prob = 0.0f, x0 = 0.0f, x1 = 0.0f, x2 = 0.0f;
-        if (alive) {
-            rays++;
-            if (!(t < INFINITY)) { // Render.cpp:146: misses leave the active list
-                finished = true;
-            } else {
-                uint32_t const material = static_cast<uint32_t>(prim) < scene.nSpheres
-                                              ? sh.sphereMaterial[prim]
-                                              : sh.planes[prim - static_cast<int32_t>(scene.nSpheres)].material;
-                Philox4 const r = philoxRender(pixel, sample, depth + 1u, 0u, cfg.keys);
-                bool const survives =
-                    shadeRoulette(sh.materials[material], depth, uniformFromBits(r.v[0]), thr, rad, prob);
-                x0 = uniformFromBits(r.v[1]), x1 = uniformFromBits(r.v[2]), x2 = uniformFromBits(r.v[3]);
-                shaded++;
-                depth += 1u; // <= kDepthLimit: a path that reaches it ends below
-                deepest = depth > deepest ? depth : deepest;
-                finished = !survives || (cfg.maxDepth && depth >= cfg.maxDepth) || depth >= kDepthLimit;
-                park = !finished;
-            }
-        }
+        // Straight-line for every lane, no branch to reconverge before the ballot below: a lane without a hit — a miss
+        // (Render.cpp:146: misses leave the active list) or a dead lane, which closestHit returns as one — draws its
+        // numbers against the scene's first material and drops the results.
+        bool const hit = t < INFINITY;
+        uint32_t material = 0;
+        if (hit)
+            material = static_cast<uint32_t>(prim) < scene.nSpheres
+                           ? sh.sphereMaterial[prim]
+                           : sh.planes[prim - static_cast<int32_t>(scene.nSpheres)].material;
+        Philox4 const r = philoxRender(pixel, sample, depth + 1u, 0u, cfg.keys);
+        float prob;
+        RGBf radNext = rad;
+        bool const survives = shadeRoulette(sh.materials[material], depth, uniformFromBits(r.v[0]), thr, radNext, prob);
+        float const x0 = uniformFromBits(r.v[1]), x1 = uniformFromBits(r.v[2]), x2 = uniformFromBits(r.v[3]);
+        rad = hit ? radNext : rad;
+        rays += alive ? 1u : 0u;
+        shaded += hit ? 1u : 0u;
+        depth += hit ? 1u : 0u; // <= kDepthLimit: a path that reaches it ends below
+        deepest = depth > deepest ? depth : deepest;
+        bool const park = hit && survives && !(cfg.maxDepth && depth >= cfg.maxDepth) && depth < kDepthLimit;
+        bool const finished = alive && !park;
         // ---- compaction #2 (Render.cpp:215-217): survivors are pushed onto the warp's queue ----
         unsigned const parkMask = __ballot_sync(kFull, park);
         if (park) {
