@@ -399,11 +399,12 @@ __global__ void CB_PERSISTENT_BOUNDS
         parked += __popc(parkMask);
         __syncwarp();
         // ---- per-pixel accumulation (Render.cpp:245-248) ----
-        if (finished) {
-            bool const nonZero = rad.r != 0.0f || rad.g != 0.0f || rad.b != 0.0f;
+        // Most paths end with nothing to add (only those that met the light carry radiance): one test for both.
+        bool const nonZero = (rad.r != 0.0f) | (rad.g != 0.0f) | (rad.b != 0.0f);
+        if (finished & nonZero) {
+            contributed++;
             bool const finite = isfinite(rad.r) && isfinite(rad.g) && isfinite(rad.b);
-            contributed += nonZero ? 1u : 0u;
-            if (nonZero && (finite || !dropNonFinite)) {
+            if (finite || !dropNonFinite) {
                 atomicAdd(&accum[pixel], make_float4(rad.r, rad.g, rad.b, 1.0f));
                 if (accum2)
                     atomicAdd(&accum2[pixel], make_float4(rad.r * rad.r, rad.g * rad.g, rad.b * rad.b, 0.0f));
