@@ -131,6 +131,20 @@ constexpr unsigned kWalkRefill = CORNELIS_WALK_REFILL; // idle lanes that trigge
 // relative instruction counts of the two kinds of step
 constexpr unsigned kWalkTestCost = CORNELIS_WALK_TEST_COST, kWalkAdvanceCost = CORNELIS_WALK_ADVANCE_COST;
 
+// 1: the walker reads its rays and writes its hit records with streaming (evict-first) accesses, leaving the L1 to
+// the grid's cell ranges and references, which are what its lanes wait for (config 4: 1533 against 1506 Msamples/s,
+// profiles/r2_walk/variants.log).
+#ifndef CORNELIS_WALK_STREAMING
+#define CORNELIS_WALK_STREAMING 1
+#endif
+#if CORNELIS_WALK_STREAMING
+#define CB_WALK_LOAD4(p) __ldcs(p)
+#define CB_WALK_STORE_HIT(p, t, prim) \
+    __stcs(reinterpret_cast<float2 *>(p), make_float2(t, __int_as_float(prim)))
+#else
+#define CB_WALK_LOAD4(p) (*(p))
+#define CB_WALK_STORE_HIT(p, t, prim) (*(p) = HitRecord{t, prim})
+#endif
 #ifndef CORNELIS_WALK_MIN_BLOCKS
 #define CORNELIS_WALK_MIN_BLOCKS 4
 #endif
@@ -181,12 +195,12 @@ __device__ __forceinline__ void walkBody(Control *ctl, const SceneView &scene, c
                 unsigned long long const mine = first + k + lane;
                 if (mine < cameraEnd) {
                     uint32_t const at = static_cast<uint32_t>(mine);
-                    float4 const o4 = pool.org[at], d4 = pool.dir[at];
+                    float4 const o4 = CB_WALK_LOAD4(pool.org + at), d4 = CB_WALK_LOAD4(pool.dir + at);
                     float tc = INFINITY; // IntersectionData::reset, Geometry.cpp:7-12
                     int32_t pc = -1;
                     closestHitGrid(true, V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, scene, sh.planes, tc, pc, nullptr,
                                    cellStart);
-                    hits[at] = HitRecord{tc, pc};
+                    CB_WALK_STORE_HIT(hits + at, tc, pc);
                 }
             }
         }
@@ -227,14 +241,14 @@ __device__ __forceinline__ void walkBody(Control *ctl, const SceneView &scene, c
                     exhausted = true;
                 } else {
                     index = static_cast<uint32_t>(mine);
-                    float4 const o4 = pool.org[index], d4 = pool.dir[index];
+                    float4 const o4 = CB_WALK_LOAD4(pool.org + index), d4 = CB_WALK_LOAD4(pool.dir + index);
                     o = V3{o4.x, o4.y, o4.z};
                     d = V3{d4.x, d4.y, d4.z};
                     t = INFINITY; // IntersectionData::reset, Geometry.cpp:7-12
                     prim = -1;
                     walking = gridWalkBegin(w, o, d, scene, sh.planes, t, prim, nullptr, cellStart);
                     if (!walking)
-                        hits[index] = HitRecord{t, prim}; // decided without a walk (degenerate, outside the grid, ...)
+                        CB_WALK_STORE_HIT(hits + index, t, prim); // decided without a walk (degenerate, outside the grid, ...)
                 }
             }
         } else if (walkMask == 0u) {
@@ -257,7 +271,7 @@ __device__ __forceinline__ void walkBody(Control *ctl, const SceneView &scene, c
                 if (wantAdvance) {
                     walking = gridWalkAdvance(w, scene.grid, t, nullptr, cellStart);
                     if (!walking)
-                        hits[index] = HitRecord{t, prim};
+                        CB_WALK_STORE_HIT(hits + index, t, prim);
                 }
                 if (__popc(__ballot_sync(kFull, !walking && !exhausted)) >= kWalkRefill)
                     break;

@@ -782,6 +782,24 @@ def test_handle_churn_reuses_device_memory(binding):
         assert np.allclose(images[0], img, rtol=1e-5, atol=1e-6)  # same paths; atomics reorder the fp32 sums
 
 
+def test_pipelines_trace_the_same_paths(binding):
+    """The wavefront stages and the persistent kernel share path identity, random numbers and arithmetic, with one
+    deliberate difference: a plane hit at t == 0 (a bounce that starts ON a wall: one ray in eight here) carries the
+    reference's sign of zero in the wavefront's hit records and whatever zero the fast division returned in the
+    persistent kernel, where t only enters P = o + d * t.  No path may notice: identical ray, hit, depth and
+    contribution counts, images equal up to fp32 summation order."""
+    sc = binding.Scene(scenes.cornell_box(aspect=0.5625))
+    for (w, h, spp, depth) in [(192, 108, 64, 0), (61, 37, 128, 0), (128, 72, 32, 5)]:
+        a = sc.render_accumulate(w, h, spp, pipeline=1, max_depth=depth)
+        img_a = sc.resolve(spp).copy()
+        b = sc.render_accumulate(w, h, spp, pipeline=2, max_depth=depth)
+        img_b = sc.resolve(spp)
+        for key in ("pixel_samples", "rays", "shaded_hits", "max_depth", "contributions"):
+            assert a[key] == b[key], (w, h, spp, key)
+        finite = np.isfinite(img_a) & np.isfinite(img_b)
+        assert finite.mean() > 0.999 and np.allclose(img_a[finite], img_b[finite], rtol=1e-4, atol=1e-5)
+
+
 def test_lane_refill_variant_traces_the_same_paths(binding, monkeypatch):
     """The persistent kernel without the queues (kept for scenes whose tables leave no shared memory for them;
     CORNELIS_PERSISTENT_QUEUE=0 selects it at scene creation) accounts for the same paths as the queued one."""
