@@ -118,8 +118,10 @@ constexpr unsigned kWalkClaim = 256;  // rays a warp claims per atomic
 #define CORNELIS_WALK_CAMERA_PHASE 1
 #endif
 constexpr unsigned kWalkCameraClaim = 128; // camera rays a warp claims per atomic in phase 1: four coherent packets
+// (8 while a refill meant setting rays up with the idle lanes; with prepared walks a refill is five shared-memory loads
+// per lane and 4-6 measure best, profiles/r2_walk/variants.log)
 #ifndef CORNELIS_WALK_REFILL
-#define CORNELIS_WALK_REFILL 8
+#define CORNELIS_WALK_REFILL 4
 #endif
 #ifndef CORNELIS_WALK_TEST_COST
 #define CORNELIS_WALK_TEST_COST 11
@@ -145,6 +147,13 @@ constexpr unsigned kWalkTestCost = CORNELIS_WALK_TEST_COST, kWalkAdvanceCost = C
 #define CB_WALK_LOAD4(p) (*(p))
 #define CB_WALK_STORE_HIT(p, t, prim) (*(p) = HitRecord{t, prim})
 #endif
+// 1: pooled rays are set up 32 at a time with every lane busy and parked, walk state included, in a queue of the warp
+// in shared memory, from which the lanes whose walks are over take them; 0: a lane sets its next ray up itself.
+#ifndef CORNELIS_WALK_PREPARED
+#define CORNELIS_WALK_PREPARED 1
+#endif
+constexpr uint32_t kWalkQueueChunks = 5; // float4 per parked walk (walkBody)
+constexpr size_t kWalkQueueBytesPerWarp = kWalkQueueChunks * 32u * sizeof(float4);
 #ifndef CORNELIS_WALK_MIN_BLOCKS
 #define CORNELIS_WALK_MIN_BLOCKS 4
 #endif
@@ -158,7 +167,7 @@ constexpr unsigned kWalkTestCost = CORNELIS_WALK_TEST_COST, kWalkAdvanceCost = C
 constexpr int kWalkSharedThreads = 1024;
 template <bool kRangesInShared>
 __device__ __forceinline__ void walkBody(Control *ctl, const SceneView &scene, const PathPool &pool,
-                                         HitRecord *__restrict__ hits, uint32_t rangesOffset) {
+                                         HitRecord *__restrict__ hits, uint32_t rangesOffset, uint32_t queueOffset) {
     extern __shared__ __align__(16) unsigned char smem[];
     SharedScene const sh = stageScene<true>(scene, smem, false);
     const uint32_t *cellStart = nullptr;
@@ -216,6 +225,94 @@ __device__ __forceinline__ void walkBody(Control *ctl, const SceneView &scene, c
     float t = INFINITY;
     int32_t prim = -1;
     GridWalk w{};
+#if CORNELIS_WALK_PREPARED
+    // The warp's queue of prepared walks: up to 32 records of five float4, chunk c of record e at [32 c + e]:
+    //   (o, t so far) (d, primitive so far) (tx, ty, tz, cell) (dtx, dty, dtz, ray index)
+    //   (tMargin, steps left per axis in 9 bits each | the three direction signs, k, last)
+    // In the pull model a lane used to set its next ray up when its walk was over — 9 lanes of 32 at a time on config 4,
+    // and 38 % of the kernel's instructions (profiles/r2_walk).  Now the warp sets 32 rays up together whenever its
+    // queue is empty and enough lanes wait, every lane busy, next to the walks the other lanes still hold in their
+    // registers; a ray that needs no walk gets its hit record at once.
+    float4 *const queue = reinterpret_cast<float4 *>(smem + queueOffset) + (threadIdx.x >> 5) * (kWalkQueueChunks * 32u);
+    unsigned qHead = 0, qCount = 0; // warp-uniform
+    bool raysLeft = n != 0;         // warp-uniform: the claims have not run past the pool yet
+    for (;;) {
+        unsigned const idleMask = __ballot_sync(kFull, !walking);
+        unsigned const walkMask = ~idleMask;
+        if (walkMask == 0u && qCount == 0u && !raysLeft)
+            break; // nothing walking, nothing parked, nothing left to claim
+        unsigned const nIdle = __popc(idleMask);
+        bool const refill = nIdle >= kWalkRefill || walkMask == 0u;
+        if (refill && qCount == 0u && raysLeft) {
+            if (stashNext == stashEnd) {
+                unsigned long long fresh = 0;
+                if (lane == 0)
+                    fresh = atomicAdd(&ctl->walkCursor, static_cast<unsigned long long>(kWalkClaim));
+                stashNext = __shfl_sync(kFull, fresh, 0);
+                stashEnd = stashNext + kWalkClaim;
+            }
+            unsigned long long const mine = stashNext + lane;
+            stashNext += 32u;
+            raysLeft = stashNext < n; // the cursor only grows: once past the pool, always past it
+            bool started = false;
+            V3 po{0.f, 0.f, 0.f}, pd{0.f, 0.f, 0.f};
+            float pt = INFINITY; // IntersectionData::reset, Geometry.cpp:7-12
+            int32_t pprim = -1;
+            GridWalk pw{};
+            uint32_t const pindex = static_cast<uint32_t>(mine);
+            if (mine < n) {
+                float4 const o4 = CB_WALK_LOAD4(pool.org + pindex), d4 = CB_WALK_LOAD4(pool.dir + pindex);
+                po = V3{o4.x, o4.y, o4.z};
+                pd = V3{d4.x, d4.y, d4.z};
+                started = gridWalkBegin(pw, po, pd, scene, sh.planes, pt, pprim, nullptr, cellStart);
+                if (!started)
+                    CB_WALK_STORE_HIT(hits + pindex, pt, pprim); // decided without a walk (degenerate, outside the grid, ...)
+            }
+            unsigned const startedMask = __ballot_sync(kFull, started);
+            if (started) {
+                unsigned const slot = __popc(startedMask & below);
+                uint32_t const packed = static_cast<uint32_t>(pw.leftX) | static_cast<uint32_t>(pw.leftY) << 9 |
+                                        static_cast<uint32_t>(pw.leftZ) << 18 | (pw.strideX > 0 ? 1u << 27 : 0u) |
+                                        (pw.strideY > 0 ? 1u << 28 : 0u) | (pw.strideZ > 0 ? 1u << 29 : 0u);
+                queue[slot] = make_float4(po.x, po.y, po.z, pt);
+                queue[32u + slot] = make_float4(pd.x, pd.y, pd.z, __int_as_float(pprim));
+                queue[64u + slot] = make_float4(pw.tx, pw.ty, pw.tz, __int_as_float(pw.cell));
+                queue[96u + slot] = make_float4(pw.dtx, pw.dty, pw.dtz, __uint_as_float(pindex));
+                queue[128u + slot] = make_float4(pw.tMargin, __uint_as_float(packed), __uint_as_float(pw.k),
+                                                 __uint_as_float(pw.last));
+            }
+            qHead = 0;
+            qCount = __popc(startedMask);
+            __syncwarp();
+        }
+        if (refill && qCount != 0u) {
+            unsigned const take = nIdle < qCount ? nIdle : qCount;
+            unsigned const rank = __popc(idleMask & below);
+            if (!walking && rank < take) {
+                unsigned const e = qHead + rank;
+                float4 const q0 = queue[e], q1 = queue[32u + e], q2 = queue[64u + e], q3 = queue[96u + e],
+                             q4 = queue[128u + e];
+                o = V3{q0.x, q0.y, q0.z}, t = q0.w;
+                d = V3{q1.x, q1.y, q1.z}, prim = __float_as_int(q1.w);
+                w.tx = q2.x, w.ty = q2.y, w.tz = q2.z, w.cell = __float_as_int(q2.w);
+                w.dtx = q3.x, w.dty = q3.y, w.dtz = q3.z, index = __float_as_uint(q3.w);
+                uint32_t const packed = __float_as_uint(q4.y);
+                int32_t const nx = static_cast<int32_t>(scene.grid.nx), nxy = static_cast<int32_t>(scene.grid.nx * scene.grid.ny);
+                w.tMargin = q4.x, w.k = __float_as_uint(q4.z), w.last = __float_as_uint(q4.w);
+                w.leftX = static_cast<int32_t>(packed & 511u), w.leftY = static_cast<int32_t>((packed >> 9) & 511u),
+                w.leftZ = static_cast<int32_t>((packed >> 18) & 511u);
+                w.strideX = (packed & (1u << 27)) ? 1 : -1, w.strideY = (packed & (1u << 28)) ? nx : -nx,
+                w.strideZ = (packed & (1u << 29)) ? nxy : -nxy;
+                w.A = dot(d, d);
+                w.rA = rcpSeedRefined(w.A);
+                w.lastTested = 0xffffffffu;
+                walking = true;
+            }
+            qHead += take;
+            qCount -= take;
+            __syncwarp(); // the records read here are overwritten by the next refill
+        }
+#else
     for (;;) {
         unsigned const idleMask = __ballot_sync(kFull, !walking && !exhausted);
         unsigned const walkMask = __ballot_sync(kFull, walking);
@@ -254,6 +351,7 @@ __device__ __forceinline__ void walkBody(Control *ctl, const SceneView &scene, c
         } else if (walkMask == 0u) {
             break; // nothing walking, nothing left to claim
         }
+#endif
         // A burst of rounds.  A walking lane wants one of two things: to TEST the next sphere of its cell (~55
         // instructions) or, when the cell has none left — empty cells are the common case — to ADVANCE to the next
         // cell (~25).  Executing both per round (one mixed step per lane) left 11.9 of 32 lanes active per instruction
@@ -273,8 +371,14 @@ __device__ __forceinline__ void walkBody(Control *ctl, const SceneView &scene, c
                     if (!walking)
                         CB_WALK_STORE_HIT(hits + index, t, prim);
                 }
+#if CORNELIS_WALK_PREPARED
+                // (leave the burst for a refill only while there is something to refill from)
+                if ((qCount != 0u || raysLeft) && __popc(__ballot_sync(kFull, !walking)) >= kWalkRefill)
+                    break;
+#else
                 if (__popc(__ballot_sync(kFull, !walking && !exhausted)) >= kWalkRefill)
                     break;
+#endif
             } else if (walking && !wantAdvance) {
                 gridWalkTest(w, o, d, scene.grid, t, prim);
             }
@@ -283,13 +387,14 @@ __device__ __forceinline__ void walkBody(Control *ctl, const SceneView &scene, c
 }
 
 __global__ void __launch_bounds__(kBlockThreads, CORNELIS_WALK_MIN_BLOCKS)
-    k_walk(Control *ctl, SceneView scene, PathPool pool, HitRecord *__restrict__ hits) {
-    walkBody<false>(ctl, scene, pool, hits, 0u);
+    k_walk(Control *ctl, SceneView scene, PathPool pool, HitRecord *__restrict__ hits, uint32_t queueOffset) {
+    walkBody<false>(ctl, scene, pool, hits, 0u, queueOffset);
 }
 
 __global__ void __launch_bounds__(kWalkSharedThreads, 1)
-    k_walk_shared(Control *ctl, SceneView scene, PathPool pool, HitRecord *__restrict__ hits, uint32_t rangesOffset) {
-    walkBody<true>(ctl, scene, pool, hits, rangesOffset);
+    k_walk_shared(Control *ctl, SceneView scene, PathPool pool, HitRecord *__restrict__ hits, uint32_t rangesOffset,
+                  uint32_t queueOffset) {
+    walkBody<true>(ctl, scene, pool, hits, rangesOffset, queueOffset);
 }
 
 // Compaction #1 for grid scenes (Render.cpp:142-149): hits to the hit queue, misses that carry radiance to the finished
@@ -741,19 +846,30 @@ void launchRaygen(cudaStream_t s, const LaunchShape &shape, const Control *ctl, 
     k_raygen<<<shape.gridRaygen, kBlockThreads, 0, s>>>(ctl, cfg, cam, pool);
 }
 
+// shared memory of the warps' queues of prepared walks behind a walker CTA's other tables
+static size_t walkQueueBytes(int threads) {
+    return CORNELIS_WALK_PREPARED ? static_cast<size_t>(threads / 32) * kWalkQueueBytesPerWarp : 0u;
+}
+
 void launchIntersect(cudaStream_t s, const LaunchShape &shape, Control *ctl, const SceneView &scene,
                      const PathPool &pool, HitRecord *hits, uint32_t *hitQueue, FinishedPath *finished) {
     if (scene.grid.enabled) {
-        if (shape.walkPull) {
-            // the cells' ranges ride in shared memory when they fit behind the scene tables (one 1024-thread CTA per SM)
+        // (a scene whose tables leave no shared memory for the walker's queues takes the one-ray-per-thread kernel)
+        bool const roomForQueues = ((shape.sceneSmemBytes + 15u) & ~static_cast<size_t>(15u)) +
+                                       walkQueueBytes(kBlockThreads) + 1024u <= shape.smemOptin;
+        if (shape.walkPull && roomForQueues) {
+            // the cells' ranges ride in shared memory when they fit behind the scene tables (one 1024-thread CTA per SM);
+            // the warps' queues of prepared walks come last
             size_t const rangesOffset = (shape.sceneSmemBytes + 15u) & ~static_cast<size_t>(15u);
             size_t const nCells = static_cast<size_t>(scene.grid.nx) * scene.grid.ny * scene.grid.nz;
-            size_t const withRanges = rangesOffset + sizeof(uint32_t) * (nCells + 1u);
-            if (shape.walkRangesInShared && withRanges + 1024u <= shape.smemOptin)
-                k_walk_shared<<<shape.numSMs, kWalkSharedThreads, withRanges, s>>>(ctl, scene, pool, hits,
-                                                                                 static_cast<uint32_t>(rangesOffset));
+            size_t const withRanges = (rangesOffset + sizeof(uint32_t) * (nCells + 1u) + 15u) & ~static_cast<size_t>(15u);
+            size_t const sharedQueues = walkQueueBytes(kWalkSharedThreads);
+            if (shape.walkRangesInShared && withRanges + sharedQueues + 1024u <= shape.smemOptin)
+                k_walk_shared<<<shape.numSMs, kWalkSharedThreads, withRanges + sharedQueues, s>>>(
+                    ctl, scene, pool, hits, static_cast<uint32_t>(rangesOffset), static_cast<uint32_t>(withRanges));
             else
-                k_walk<<<shape.gridWalk, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, scene, pool, hits);
+                k_walk<<<shape.gridWalk, kBlockThreads, rangesOffset + walkQueueBytes(kBlockThreads), s>>>(
+                    ctl, scene, pool, hits, static_cast<uint32_t>(rangesOffset));
             k_compact_hits<<<shape.gridAccumulate, kBlockThreads, 0, s>>>(ctl, pool, hits, hitQueue, finished);
         } else {
             k_intersect<true><<<shape.gridIntersectGrid, kBlockThreads, shape.sceneSmemBytes, s>>>(ctl, scene, pool, hits,
@@ -930,7 +1046,8 @@ cudaError_t configureKernels(LaunchShape &shape) {
         return e;
     if ((e = resident(k_intersect<true>, shape.sceneSmemBytes, shape.gridIntersectGrid)) != cudaSuccess)
         return e;
-    if ((e = resident(k_walk, shape.sceneSmemBytes, shape.gridWalk)) != cudaSuccess)
+    if ((e = resident(k_walk, ((shape.sceneSmemBytes + 15u) & ~static_cast<size_t>(15u)) + walkQueueBytes(kBlockThreads),
+                      shape.gridWalk)) != cudaSuccess)
         return e;
     if (const char *env = std::getenv("CORNELIS_WALK_PULL"))
         shape.walkPull = std::atoi(env) != 0;
