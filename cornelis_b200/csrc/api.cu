@@ -647,6 +647,10 @@ int cornelis_cuda_render_accumulate(cornelis_cuda_scene *s, const cornelis_rende
     cfg.dx = 1.0f / static_cast<float>(p->width);  // Render.cpp:31
     cfg.dy = 1.0f / static_cast<float>(p->height);
     cfg.byWidth = makeFastDiv(cfg.width);
+    cfg.tilesPerRow = (CORNELIS_RAYGEN_TILES && cfg.width % kTileWidth == 0u && cfg.height % kTileHeight == 0u)
+                          ? cfg.width / kTileWidth
+                          : 0u;
+    cfg.byTilesPerRow = makeFastDiv(cfg.tilesPerRow ? cfg.tilesPerRow : 1u);
     cfg.keys = makePhiloxKeys(cfg.key0, cfg.key1);
 
     Control init{};

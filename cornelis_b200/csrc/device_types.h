@@ -52,6 +52,21 @@ struct DevCamera {   // PerspectiveCamera (Camera.hpp:57-60), produced by lookAt
     float vx, vy, vz, pad3;
 };
 
+// 1: the wavefront pipeline generates camera paths in 8x4-pixel tiles (RenderConfig::tilesPerRow); 0: in row order.
+#ifndef CORNELIS_RAYGEN_TILES
+#define CORNELIS_RAYGEN_TILES 1
+#endif
+#ifndef CORNELIS_RAYGEN_TILE_SHIFT
+#define CORNELIS_RAYGEN_TILE_SHIFT 3 // log2 of the tile width: 8 x 4 pixels
+#endif
+constexpr unsigned kTileWidth = 1u << CORNELIS_RAYGEN_TILE_SHIFT, kTileHeight = 32u / kTileWidth;
+
+// 1: the walk's termination slack follows the ray's best hit so far (geometry.cuh); 0: one worst-case slack for the
+// whole trusted region (round 1).
+#ifndef CORNELIS_GRID_RAY_MARGIN
+#define CORNELIS_GRID_RAY_MARGIN 1
+#endif
+
 // Uniform grid over the spheres.  Every sphere is listed, by ascending index, in every cell
 // its padded bounding box overlaps; closestHitGrid walks the cells a ray crosses front to back and runs the SAME
 // per-sphere test on the listed spheres, so hit ids and t are those of the exhaustive scan (see geometry.cuh for the
@@ -63,7 +78,9 @@ struct DevGrid {
     float invx, invy, invz;        // their reciprocals
     float rminx, rminy, rminz;     // "trusted region": ray origins inside it are covered by the error bound the
     float rmaxx, rmaxy, rmaxz;     //   padding was derived from; other rays take the exhaustive scan
-    float margin;                  // slack (a distance) on the front-to-back termination test
+    float margin;                  // slack (a distance) on the front-to-back termination test: the part that does not
+                                   //   depend on the hit so far (geometry.cuh: per-ray margin)
+    float marginScale;             // 1 + slope: the walk stops when t_best * marginScale + margin / |d| < t(cell exit)
     uint32_t nx, ny, nz;           // resolution
     uint32_t enabled;              // 0: scan all spheres from shared memory
     const uint2 *cellRange;        // per cell: [first, last) into the two reference arrays
@@ -163,6 +180,10 @@ struct RenderConfig {
     uint32_t key0, key1; // Philox key = seed
     float dx, dy;       // 1.0f / width, 1.0f / height (Render.cpp:31)
     FastDiv byWidth;    // pixel -> row without a software divide
+    // Wavefront pipeline: camera paths are generated in 8x4-pixel tiles (32 consecutive paths = one tile) when the frame
+    // divides into them, so that a warp's camera rays cross the same cells of the grid (k_raygen); 0: row order.
+    uint32_t tilesPerRow;
+    FastDiv byTilesPerRow;
     PhiloxKeys keys;    // the ten Philox round keys of (key0, key1)
 };
 

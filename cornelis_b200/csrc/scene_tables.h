@@ -226,7 +226,19 @@ inline bool buildGrid(const cornelis_sphere_desc *spheres, size_t n, const doubl
         g.rminx = std::nextafterf(static_cast<float>(rmin[0]), INFINITY), g.rmaxx = std::nextafterf(static_cast<float>(rmax[0]), -INFINITY);
         g.rminy = std::nextafterf(static_cast<float>(rmin[1]), INFINITY), g.rmaxy = std::nextafterf(static_cast<float>(rmax[1]), -INFINITY);
         g.rminz = std::nextafterf(static_cast<float>(rmin[2]), INFINITY), g.rmaxz = std::nextafterf(static_cast<float>(rmax[2]), -INFINITY);
+#if CORNELIS_GRID_RAY_MARGIN
+        // Per-ray termination slack (geometry.cuh): 2 sqrt(kappa) (t_best |d| + r_max) with kappa = 2^-19, inflated by
+        // 1.003 (|o - c| against t |d| + r, see there) and 1 % for the roundings of the slack itself.
+        double rmaxSphere = 0;
+        for (size_t i = 0; i < n; i++)
+            rmaxSphere = std::max(rmaxSphere, std::fabs(static_cast<double>(spheres[i].radius)));
+        double const slope = 2.0 * std::sqrt(std::ldexp(1.0, -19)) * 1.003 * 1.01;
+        g.margin = static_cast<float>(slope * rmaxSphere + 1e-6 * D);
+        g.marginScale = std::nextafterf(static_cast<float>(1.0 + slope), INFINITY);
+#else
         g.margin = static_cast<float>(2.0 * std::sqrt(eps) * 1.001);
+        g.marginScale = 1.0f;
+#endif
         g.nx = dim[0], g.ny = dim[1], g.nz = dim[2];
         g.enabled = 1;
         out.cellRange.swap(ranges);

@@ -14,7 +14,8 @@ __global__ void k_plan(Control *ctl, RenderConfig cfg) {
     uint32_t const survivors = ctl->nSurvive;
     unsigned long long const remaining = ctl->total - ctl->cursor;
     uint32_t const room = cfg.poolPaths - survivors;
-    uint32_t const gen = remaining < room ? static_cast<uint32_t>(remaining) : room;
+    // (tiled generation: whole tiles of 32 paths, so that every warp of k_raygen and k_walk holds one tile)
+    uint32_t const gen = remaining < room ? static_cast<uint32_t>(remaining) : cfg.tilesPerRow ? room & ~31u : room;
     ctl->genBase = survivors;
     ctl->genCount = gen;
     ctl->genFirst = ctl->cursor;
@@ -46,7 +47,16 @@ __global__ void __launch_bounds__(kBlockThreads) k_raygen(const Control *ctl, Re
         uint32_t const wraps = pixel / cfg.npixels;
         pixel -= wraps * cfg.npixels;
         uint32_t const sample = cfg.firstSample + sample0 + wraps;
-        uint32_t const j = fastDivide(pixel, cfg.byWidth), i = pixel - j * cfg.width;
+        uint32_t j, i;
+        if (cfg.tilesPerRow) { // `pixel` so far is the position in tile order: tile = pixel / 32, 8 x 4 pixels each
+            uint32_t const tile = pixel >> 5, within = pixel & 31u;
+            uint32_t const tileRow = fastDivide(tile, cfg.byTilesPerRow), tileCol = tile - tileRow * cfg.tilesPerRow;
+            i = tileCol * kTileWidth + (within & (kTileWidth - 1u));
+            j = tileRow * kTileHeight + (within >> CORNELIS_RAYGEN_TILE_SHIFT);
+            pixel = j * cfg.width + i;
+        } else {
+            j = fastDivide(pixel, cfg.byWidth), i = pixel - j * cfg.width;
+        }
         Philox4 const r = philoxRender(pixel, sample, 0u, 0u, cfg.keys);
         float const phi1 = uniformFromBits(r.v[0]), phi2 = uniformFromBits(r.v[1]); // Render.cpp:94-95
         V3 const d = pixelRayDirection(cam, i, j, cfg.dx, cfg.dy, phi1, phi2);
@@ -154,6 +164,9 @@ constexpr unsigned kWalkTestCost = CORNELIS_WALK_TEST_COST, kWalkAdvanceCost = C
 #endif
 constexpr uint32_t kWalkQueueChunks = 5; // float4 per parked walk (walkBody)
 constexpr size_t kWalkQueueBytesPerWarp = kWalkQueueChunks * 32u * sizeof(float4);
+#ifndef CORNELIS_WALK_LEAN_ROUNDS
+#define CORNELIS_WALK_LEAN_ROUNDS 1
+#endif
 #ifndef CORNELIS_WALK_MIN_BLOCKS
 #define CORNELIS_WALK_MIN_BLOCKS 4
 #endif
@@ -236,9 +249,15 @@ __device__ __forceinline__ void walkBody(Control *ctl, const SceneView &scene, c
     float4 *const queue = reinterpret_cast<float4 *>(smem + queueOffset) + (threadIdx.x >> 5) * (kWalkQueueChunks * 32u);
     unsigned qHead = 0, qCount = 0; // warp-uniform
     bool raysLeft = n != 0;         // warp-uniform: the claims have not run past the pool yet
+    // The lanes that hold a walk, warp-uniform and kept up to date where it changes (a refill, a round of advances): the
+    // rounds below then cost ONE vote each (CORNELIS_WALK_LEAN_ROUNDS; 0: the round-1 loop that votes on both kinds of
+    // step every round and leaves the burst every 32 rounds).
+    unsigned walkMask = 0u;
     for (;;) {
-        unsigned const idleMask = __ballot_sync(kFull, !walking);
-        unsigned const walkMask = ~idleMask;
+#if !CORNELIS_WALK_LEAN_ROUNDS
+        walkMask = __ballot_sync(kFull, walking);
+#endif
+        unsigned const idleMask = ~walkMask;
         if (walkMask == 0u && qCount == 0u && !raysLeft)
             break; // nothing walking, nothing parked, nothing left to claim
         unsigned const nIdle = __popc(idleMask);
@@ -311,7 +330,37 @@ __device__ __forceinline__ void walkBody(Control *ctl, const SceneView &scene, c
             qHead += take;
             qCount -= take;
             __syncwarp(); // the records read here are overwritten by the next refill
+            walkMask = __ballot_sync(kFull, walking);
         }
+#if CORNELIS_WALK_LEAN_ROUNDS
+        // A burst of rounds (see below for the two kinds of step and why a round runs only one of them).  Lanes finish
+        // only in a round of advances and start only in a refill, so the set of walking lanes is re-voted there and
+        // nowhere else: a round of tests costs one vote, one population count and one compare on top of the test.
+        // nAdvance * kWalkTestCost >= nTest * kWalkAdvanceCost with nTest = nWalk - nAdvance.
+        {
+            unsigned nWalk = __popc(walkMask);
+#pragma unroll 1
+            while (nWalk != 0u) {
+                bool const wantAdvance = walking && w.k >= w.last;
+                unsigned const nAdvance = __popc(__ballot_sync(kFull, wantAdvance));
+                if (nAdvance * (kWalkTestCost + kWalkAdvanceCost) >= nWalk * kWalkAdvanceCost) {
+                    if (wantAdvance) {
+                        walking = gridWalkAdvance(w, scene.grid, t, nullptr, cellStart);
+                        if (!walking)
+                            CB_WALK_STORE_HIT(hits + index, t, prim);
+                    }
+                    walkMask = __ballot_sync(kFull, walking);
+                    nWalk = __popc(walkMask);
+                    // (leave the burst for a refill only while there is something to refill from)
+                    if ((qCount != 0u || raysLeft) && 32u - nWalk >= kWalkRefill)
+                        break;
+                } else if (walking && !wantAdvance) {
+                    gridWalkTest(w, o, d, scene.grid, t, prim);
+                }
+            }
+        }
+        continue;
+#endif
 #else
     for (;;) {
         unsigned const idleMask = __ballot_sync(kFull, !walking && !exhausted);

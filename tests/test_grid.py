@@ -154,3 +154,42 @@ def test_grid_terminates_early(grid_host):
     hit = got["prim"] >= 0
     assert got["cells"][hit].mean() < 0.6 * got["cells"][~hit].mean() + 2
     assert got["cells"].max() <= nx + ny + nz + 3
+
+
+def grazing_rays(rng, flat, n, spread):
+    """Rays aimed at the silhouette of random spheres: the computed discriminant is zero up to rounding, which is the case
+    the registration radius (eps) and the termination slack exist for.  `spread` perturbs the aim relative to the radius."""
+    sph = flat["spheres"]
+    pick = rng.integers(0, len(sph), n)
+    c, r = sph[pick, :3].astype(np.float64), sph[pick, 3].astype(np.float64)
+    lo = np.array([-1900.0, 1.0, -2400.0])
+    hi = np.array([1900.0, 2020.0, 1900.0])
+    org = rng.uniform(lo, hi, (n, 3))
+    to_c = c - org
+    dist = np.linalg.norm(to_c, axis=1)
+    keep = dist > 1.5 * r
+    axis = to_c / dist[:, None]
+    # a unit vector perpendicular to the axis, then the tangent direction: angle asin(r / dist) off the axis
+    rnd = rng.standard_normal((n, 3))
+    perp = rnd - (rnd * axis).sum(axis=1, keepdims=True) * axis
+    perp /= np.linalg.norm(perp, axis=1, keepdims=True)
+    sin_a = np.clip(r / dist * (1.0 + spread * rng.standard_normal(n)), 0.0, 0.999)
+    cos_a = np.sqrt(1.0 - sin_a * sin_a)
+    d = axis * cos_a[:, None] + perp * sin_a[:, None]
+    return org[keep].astype(np.float32), d[keep].astype(np.float32)
+
+
+@pytest.mark.parametrize("n_spheres,scale", [(10000, 1.0), (1500, 1.0), (1500, 40.0)])
+def test_grid_grazing_rays(grid_host, port_oracle, n_spheres, scale):
+    """Tangent rays, from near and far origins, unit and scaled directions: the walk's per-ray termination slack
+    (geometry.cuh) and the registration radius must still deliver the exhaustive scan's hit bit for bit."""
+    flat = scenes.many_spheres(n_spheres)
+    ref = port_oracle.scene(flat)
+    rng = np.random.default_rng(23)
+    parts = [grazing_rays(rng, flat, 6000, s) for s in (0.0, 1e-7, 1e-5, 1e-3)]
+    org, dirs = np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+    dirs = (dirs * np.float32(scale)).astype(np.float32)
+    want = ref.intersect(org, dirs)
+    got = walk_grid(grid_host, flat, org, dirs)
+    check_same(got, want)
+    assert ((want["prim"] >= 0) & (want["prim"] < n_spheres)).mean() > 0.3
