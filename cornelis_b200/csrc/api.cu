@@ -116,7 +116,8 @@ class DeviceCache {
         size_t const g = bytes < (1u << 20) ? 512u : (1u << 20);
         return (std::max<size_t>(bytes, 1) + g - 1) / g * g;
     }
-    static constexpr size_t kCacheLimitBytes = size_t(8) << 30;
+    // (16 GiB: the wavefront pipeline's 2^26-path pools and queues, 11 GB, are recycled between handles too)
+    static constexpr size_t kCacheLimitBytes = size_t(16) << 30;
     std::mutex mutex_;
     std::map<int, std::multimap<size_t, void *>> free_; // device -> size -> block
     std::map<void *, size_t> sizes_;                    // blocks handed out
@@ -268,6 +269,9 @@ namespace {
 PathPool poolView(cornelis_cuda_scene *s, int which) {
     return PathPool{s->pool[which][0].ptr, s->pool[which][1].ptr, s->pool[which][2].ptr, s->pool[which][3].ptr};
 }
+
+// device memory per pooled path: two pools of four float4, a hit record, a hit-queue slot, two finished-path records
+constexpr size_t kPoolBytesPerPath = 2 * 4 * sizeof(float4) + sizeof(HitRecord) + sizeof(uint32_t) + 2 * sizeof(FinishedPath);
 
 int ensureFrame(cornelis_cuda_scene *s, uint32_t width, uint32_t height, uint32_t poolPaths, bool variance) {
     size_t const npix = static_cast<size_t>(width) * height;
@@ -602,11 +606,23 @@ int cornelis_cuda_render_accumulate(cornelis_cuda_scene *s, const cornelis_rende
         return fail(CORNELIS_ERR_INVALID_ARGUMENT, "unknown pipeline");
     bool const persistent = pipeline == CORNELIS_PIPELINE_PERSISTENT;
 
-    // Paths in flight: 2^24 (2.9 GB of pool and queues out of 180 GB).  A pass is five or six dependent launches, each
-    // of which has to drain before the next starts, and a pass of k_walk ends with a few warps still on their longest
-    // walks; with 2^22 paths those per-pass costs were 8 % of the Cornell wavefront render (4867 -> 5251 Msamples/s) and
-    // 17 % of config 4 (1262 -> 1473); 2^26 would add another 2-4 %.
+    // Paths in flight: 2^26 (10.5 GB of pools and queues out of 180 GB) when a quarter of the free device memory
+    // holds them, else 2^25, else 2^24.  A pass is five or six dependent launches, each of which has to drain before the
+    // next starts, and a pass of k_walk ends with a few warps still on their longest walks; with 2^22 paths those per-pass
+    // costs were 8 % of the Cornell wavefront render (4867 -> 5251 Msamples/s at 2^24) and 17 % of config 4 (1262 ->
+    // 1473); config 4 at the end of round 2: 1874 / 1908 / 1933 Msamples/s with 2^24 / 2^25 / 2^26.
     uint32_t pool = p->pool_paths > 0 ? static_cast<uint32_t>(p->pool_paths) : (1u << 24);
+    if (p->pool_paths <= 0 && !persistent) {
+        size_t freeBytes = 0, totalBytes = 0;
+        CB_CUDA(cudaMemGetInfo(&freeBytes, &totalBytes));
+        for (uint32_t shift = 26; shift > 24; shift--) {
+            size_t const paths = static_cast<size_t>(1) << shift;
+            if (s->pool[0][0].count >= paths || paths * kPoolBytesPerPath * 4u <= freeBytes) {
+                pool = static_cast<uint32_t>(paths);
+                break;
+            }
+        }
+    }
     if (const char *env = std::getenv("CORNELIS_POOL_PATHS"))
         if (p->pool_paths <= 0 && std::atoll(env) > 0)
             pool = static_cast<uint32_t>(std::atoll(env));

@@ -191,6 +191,23 @@ CB_HD V3 cameraDirection(const DevCamera &c, float x, float y) {
 }
 
 // NormalizedFrameBufferCoord + the jittered film position of Render.cpp:29-37, 96.
+// Camera paths are numbered sample by sample and, within a sample, by POSITION: position p of a frame is pixel p in row
+// order, or — when the frame divides into tiles of 32 pixels (RenderConfig::tilesPerRow != 0) — pixel (p & 31) of tile
+// p / 32, tiles in row order.  32 consecutive paths, one warp's worth, then cover a compact tile instead of a strip of a
+// row: their rays cross the same cells of the grid and meet the same primitives.  A bijection of the frame either way,
+// so every (pixel, sample) pair is still generated exactly once, with the random numbers of its (pixel, sample) key.
+__device__ __forceinline__ uint32_t pixelOfPosition(uint32_t position, const RenderConfig &cfg, uint32_t &i, uint32_t &j) {
+    if (cfg.tilesPerRow) {
+        uint32_t const tile = position >> 5, within = position & 31u;
+        uint32_t const tileRow = fastDivide(tile, cfg.byTilesPerRow), tileCol = tile - tileRow * cfg.tilesPerRow;
+        i = tileCol * kTileWidth + (within & (kTileWidth - 1u));
+        j = tileRow * kTileHeight + (within >> CORNELIS_RAYGEN_TILE_SHIFT);
+        return j * cfg.width + i;
+    }
+    j = fastDivide(position, cfg.byWidth), i = position - j * cfg.width;
+    return position;
+}
+
 CB_HD V3 pixelRayDirection(const DevCamera &c, uint32_t i, uint32_t j, float dx, float dy, float phi1, float phi2) {
     float x = static_cast<float>(i) * dx;
     float y = static_cast<float>(j) * dy;

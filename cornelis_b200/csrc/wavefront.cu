@@ -48,15 +48,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_raygen(const Control *ctl, Re
         pixel -= wraps * cfg.npixels;
         uint32_t const sample = cfg.firstSample + sample0 + wraps;
         uint32_t j, i;
-        if (cfg.tilesPerRow) { // `pixel` so far is the position in tile order: tile = pixel / 32, 8 x 4 pixels each
-            uint32_t const tile = pixel >> 5, within = pixel & 31u;
-            uint32_t const tileRow = fastDivide(tile, cfg.byTilesPerRow), tileCol = tile - tileRow * cfg.tilesPerRow;
-            i = tileCol * kTileWidth + (within & (kTileWidth - 1u));
-            j = tileRow * kTileHeight + (within >> CORNELIS_RAYGEN_TILE_SHIFT);
-            pixel = j * cfg.width + i;
-        } else {
-            j = fastDivide(pixel, cfg.byWidth), i = pixel - j * cfg.width;
-        }
+        pixel = pixelOfPosition(pixel, cfg, i, j); // (so far the position within the frame)
         Philox4 const r = philoxRender(pixel, sample, 0u, 0u, cfg.keys);
         float const phi1 = uniformFromBits(r.v[0]), phi2 = uniformFromBits(r.v[1]); // Render.cpp:94-95
         V3 const d = pixelRayDirection(cam, i, j, cfg.dx, cfg.dy, phi1, phi2);
@@ -119,15 +111,25 @@ __global__ void __launch_bounds__(kBlockThreads, CORNELIS_INTERSECT_MIN_BLOCKS) 
 // Walking the grid costs anything from a handful to a hundred steps per ray, and with one ray per thread a warp waits
 // for its longest walk: ncu on the one-ray-per-lane form shows 7.7 of 32 lanes active per instruction on config 4
 // (profiles/r1_diet).  k_walk is a persistent kernel of warps that PULL rays: a lane whose walk is over takes the
-// next pooled ray (a warp claims indices 256 at a time with one atomic, like the persistent pipeline's camera paths),
+// next pooled ray (a warp claims indices 64 at a time with one atomic, like the persistent pipeline's camera paths),
 // so all lanes keep stepping until the pool is drained.  Refills are batched — they run when a quarter of the warp is
 // idle — because setting up a walk (plane tests, clipping, DDA) is itself ~150 instructions.  Only the hit records are
 // written here; k_compact_hits builds the queues (compaction #1) in a streaming pass.
-constexpr unsigned kWalkClaim = 256;  // rays a warp claims per atomic
+#ifndef CORNELIS_WALK_CLAIM
+#define CORNELIS_WALK_CLAIM 64
+#endif
+// rays a warp claims per atomic (a multiple of 32).  Small claims keep the warps of an SM on neighbouring stretches of the
+// pool — whose paths, generated tile by tile, are neighbours in the scene — and shorten the tail of a pass: config 4 with
+// 512 / 256 / 128 / 64 / 32: 1725 / 1800 / 1834 / 1852 / 1852 Msamples/s (profiles/r2_walk/variants.log).
+constexpr unsigned kWalkClaim = CORNELIS_WALK_CLAIM;
+static_assert(kWalkClaim % 32u == 0u && kWalkClaim != 0u, "the prepared walks are set up 32 at a time");
 #ifndef CORNELIS_WALK_CAMERA_PHASE
 #define CORNELIS_WALK_CAMERA_PHASE 1
 #endif
-constexpr unsigned kWalkCameraClaim = 128; // camera rays a warp claims per atomic in phase 1: four coherent packets
+#ifndef CORNELIS_WALK_CAMERA_CLAIM
+#define CORNELIS_WALK_CAMERA_CLAIM 128
+#endif
+constexpr unsigned kWalkCameraClaim = CORNELIS_WALK_CAMERA_CLAIM; // camera rays a warp claims per atomic in phase 1: four coherent packets
 // (8 while a refill meant setting rays up with the idle lanes; with prepared walks a refill is five shared-memory loads
 // per lane and 4-6 measure best, profiles/r2_walk/variants.log)
 #ifndef CORNELIS_WALK_REFILL
@@ -325,6 +327,9 @@ __device__ __forceinline__ void walkBody(Control *ctl, const SceneView &scene, c
                 w.A = dot(d, d);
                 w.rA = rcpSeedRefined(w.A);
                 w.lastTested = 0xffffffffu;
+#if CORNELIS_GRID_MAILBOX2
+                w.prevTested = 0xffffffffu;
+#endif
                 walking = true;
             }
             qHead += take;

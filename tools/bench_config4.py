@@ -21,6 +21,7 @@ ap.add_argument("--spp", type=int, default=1024)
 ap.add_argument("--spheres", type=int, default=10000)
 ap.add_argument("--no-cpu", action="store_true")
 ap.add_argument("--no-exhaustive", action="store_true")
+ap.add_argument("--no-persistent", action="store_true")
 args = ap.parse_args()
 
 W, H = args.width, args.height
@@ -30,6 +31,8 @@ out = {"workload": f"{args.spheres} spheres + floor, 64 materials, {W}x{H}, {arg
        "acceleration": scene.acceleration()}
 scene.render_accumulate(W, H, 4, max_depth=64)  # warm-up
 for name, pipeline in (("persistent", binding.PIPELINE_PERSISTENT), ("wavefront", binding.PIPELINE_WAVEFRONT)):
+    if name == "persistent" and args.no_persistent:
+        continue
     st = scene.render_accumulate(W, H, args.spp, max_depth=64, pipeline=pipeline, stage_timing=True)
     out[name] = {"stage_ms_per_pass": {k: st[k] for k in ("raygen_ms", "intersect_ms", "shade_ms", "accumulate_ms")},"msamples_per_s": st["pixel_samples"] / st["gpu_ms"] / 1e3, "mrays_per_s": st["rays"] / st["gpu_ms"] / 1e3,
                  "gpu_ms": st["gpu_ms"], "rays_per_sample": st["rays"] / st["pixel_samples"], "max_depth": st["max_depth"],
