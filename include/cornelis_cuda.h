@@ -100,7 +100,8 @@ typedef struct cornelis_render_params {
     uint64_t seed;           /* PRNG::DefaultSeed = 19791102 (PRNG.hpp:12) */
     uint32_t flags;          /* CORNELIS_RENDER_* */
     int32_t pipeline;        /* CORNELIS_PIPELINE_* */
-    int32_t pool_paths;      /* paths in flight (wavefront width); 0 = default */
+    int32_t pool_paths;      /* paths in flight (wavefront width); 0 = default: 2^26, 2^25 or 2^24, the largest whose
+                                pools and queues (172 bytes per path) fit a quarter of the free device memory */
     int32_t reserved;
 } cornelis_render_params;
 
