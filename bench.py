@@ -118,59 +118,92 @@ def load_ncu(kernel):
 # ------------------------------------------------------------------------------------------------- clocks --
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons DURING the timed region."""
+    """nvidia-smi clocks and throttle reasons DURING the timed region.
+
+    nvidia-smi takes up to a second to print its first line (longer on an 8-GPU box), and at N = 8 the timed region of
+    the strong-scaling run is 0.3 s: a sampler started with the region never saw it.  So the process is started once,
+    as soon as the device is chosen, every line is stamped on arrival, and `summary()` keeps the lines that arrived
+    inside the window `with sampler.window():` bracketed (grown by one sampling period on either side, which is the
+    resolution of the stamps).  If the window was still shorter than the gaps between lines, the line nearest to it
+    is used and the distance is reported (`nearest_sample_s`)."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+    PERIOD_S = 0.1
 
     def __init__(self, device_index: int):
         self.device_index = device_index
-        self.lines = []
+        self.lines = []  # (arrival time, text)
+        self.t0 = self.t1 = None
         self.proc = None
-
-    def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.device_index)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", str(int(self.PERIOD_S * 1000)), "-i", str(self.device_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
-        return self
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
+
+    def window(self):
+        return self
+
+    def __enter__(self):
+        self.t0 = time.monotonic()
+        return self
 
     def __exit__(self, *exc):
+        self.t1 = time.monotonic()
+
+    def close(self):
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
+            self.proc = None
+
+    @staticmethod
+    def _parse(line):
+        parts = [p.strip() for p in line.split(",")]
+        if len(parts) < 8:
+            return None
+        try:
+            return float(parts[1]), float(parts[2]), float(parts[3]), parts[4:8]
+        except ValueError:
+            return None
 
     def summary(self):
-        sm, smax, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 8:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                smax.append(float(parts[2]))
-                power.append(float(parts[3]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
-                "power_w_max": max(power), "samples": len(sm)}
+        empty = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.t0 is None or self.t1 is None:
+            return empty
+        deadline = time.monotonic() + 2.0  # a line after the window, if none has come yet
+        while self.proc and time.monotonic() < deadline and not any(t >= self.t1 for t, _ in list(self.lines)):
+            time.sleep(0.05)
+        parsed = [(t, self._parse(text)) for t, text in list(self.lines)]
+        parsed = [(t, v) for t, v in parsed if v is not None]
+        if not parsed:
+            return empty
+        inside = [(t, v) for t, v in parsed if self.t0 - self.PERIOD_S <= t <= self.t1 + self.PERIOD_S]
+        out = {}
+        if not inside:
+            def distance(item):
+                t = item[0]
+                return self.t0 - t if t < self.t0 else t - self.t1
+            nearest = min(parsed, key=distance)
+            inside = [nearest]
+            out["nearest_sample_s"] = round(distance(nearest), 3)
+        sm = [v[0] for _, v in inside]
+        reasons = {name for _, v in inside for name, val in zip(names, v[3]) if val.lower().startswith("active")}
+        out.update({"sm_mhz": statistics.median(sm), "sm_max_mhz": max(v[1] for _, v in inside),
+                    "reasons": sorted(reasons), "power_w_max": max(v[2] for _, v in inside), "samples": len(sm)})
+        return out
 
 
 # ------------------------------------------------------------------------------------------ reference (CPU) --
@@ -533,6 +566,7 @@ def ours(args, flat):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
+    sampler = ClockSampler(local_rank)  # started early: its first line takes about a second
     comm = None
     if world > 1:
         # torch.distributed: rendezvous, barriers, max-over-ranks of the timings.  The data plane is the library's own
@@ -627,8 +661,10 @@ def ours(args, flat):
         step_device()
     launches[0] = 0
     collected = []
-    with ClockSampler(local_rank) as clocks:
+    with sampler.window():
         dev_s, wall_s = timed(lambda: step_device(collected), args.steps)
+    clocks_summary = sampler.summary()
+    sampler.close()
     timed_launches = launches[0]
     scene_bytes = step_e2e()  # warm the allocation path once
     e2e_dev_s, e2e_wall_s = timed(step_e2e, args.steps)
@@ -688,7 +724,7 @@ def ours(args, flat):
         "gpu_launches": int(timed_launches),
         "roofline": roofline(collected, hbm_peak, hbm_source, persistent),
         "pipeline": "persistent" if persistent else "wavefront",
-        "clocks": clocks.summary(),
+        "clocks": clocks_summary,
         "max_depth": max(s["max_depth"] for s in collected),
         "host_threads": cores,
     }
