@@ -129,7 +129,7 @@ class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
-    PERIOD_S = 0.1
+    PERIOD_S = 0.2
 
     def __init__(self, device_index: int):
         self.device_index = device_index

@@ -63,7 +63,7 @@ def test_clock_sampler_windows_by_arrival_time(tmp_path, monkeypatch):
         time.sleep(0.45)
     got = s.summary()
     s.close()
-    assert 2 <= got["samples"] <= 9 and got["sm_mhz"] == 1965.0 and got["sm_max_mhz"] == 1980.0
+    assert 2 <= got["samples"] <= 12 and got["sm_mhz"] == 1965.0 and got["sm_max_mhz"] == 1980.0
     assert got["reasons"] == ["sw_power_cap"] and "nearest_sample_s" not in got
 
     s = bench.ClockSampler(0)       # the window closes before the first line arrives
