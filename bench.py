@@ -665,7 +665,11 @@ def ours(args, flat):
     collected = []
     with sampler.window():
         dev_s, wall_s = timed(lambda: step_device(collected), args.steps)
-    clocks_summary = sampler.summary()
+    try:
+        clocks_summary = sampler.summary()
+    except Exception as e:  # the clocks block is evidence beside the measurement: never the reason a bench line is lost
+        clocks_summary = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0,
+                          "error": f"{type(e).__name__}: {e}"}
     sampler.close()
     timed_launches = launches[0]
     scene_bytes = step_e2e()  # warm the allocation path once
